@@ -1,0 +1,126 @@
+/* uob_rt.h — C ABI of the B200-native render path.
+ *
+ * This is the seam the reference crosses with OpenCL: `opencl_initialise`
+ * (Source/skeleton.cpp:366-497) and `offload_rendering` (:146-182) around the
+ * one device kernel `draw` (Source/kernels.cl:368-428).  Every entry point
+ * below names the reference code it replaces.  Plain pointers and sizes only;
+ * no C++ or torch types.  All functions are thread-compatible per context (one
+ * host thread per rt_ctx, like the reference's single in-order queue).
+ *
+ * Error convention: functions return RT_OK (0) or an RT_ERR_* code and record a
+ * message retrievable with rt_last_error(); the reference instead prints
+ * "OpenCL error during '<op>' on line N" and exits (skeleton.cpp:499-507) — the
+ * C++ host in uob_raytracer_b200/csrc/host keeps that print-and-exit behaviour
+ * on top of these codes.  There is NO CPU fallback: without a CUDA device
+ * rt_create() fails.
+ */
+#ifndef UOB_RT_H
+#define UOB_RT_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct rt_ctx rt_ctx;
+
+enum {
+  RT_OK = 0,
+  RT_ERR_INVALID = 1,  /* bad argument */
+  RT_ERR_CUDA = 2,     /* a CUDA runtime call failed (message has the op and cudaError) */
+  RT_ERR_NO_SCENE = 3, /* rt_render before rt_upload_scene */
+  RT_ERR_NO_DEVICE = 4 /* no usable CUDA device */
+};
+
+/* rt_config.flags */
+enum {
+  /* Arithmetic exactly as the CPU oracle: IEEE binary32, reference operation
+   * order, no FMA contraction, IEEE 1/x and sqrt.  Frames are bit-identical to
+   * oracle/cornell_oracle.c.  Off = the fast path (FMA, MUFU reciprocals,
+   * division-free shadow tests), within 1/255 on >= 99.9 % of pixels. */
+  RT_FLAG_STRICT_IEEE = 1u << 0,
+  RT_FLAG_FORCE_BRUTE = 1u << 1, /* never build a BVH, whatever the triangle count */
+  RT_FLAG_FORCE_BVH = 1u << 2    /* always traverse a BVH, even for 26 triangles */
+};
+
+/* Everything that is a compile-time constant in the reference
+ * (skeleton.cpp:27-34, kernels.cl:12-17, :316, :343) plus the row tile this
+ * context renders. */
+typedef struct rt_config {
+  int width, height;  /* SCREEN_WIDTH / SCREEN_HEIGHT of the whole frame */
+  int aa;             /* rays_x = rays_y (kernels.cl:12-13); aa_rays = aa*aa */
+  int shadow_samples; /* light_sources (kernels.cl:316) */
+  int max_bounces;    /* bounces (kernels.cl:343) */
+  int device;         /* CUDA ordinal; the reference picks via OCL_DEVICE (skeleton.cpp:551) */
+  int row0, rows;     /* this context renders frame rows [row0, row0+rows); rows<=0 = whole frame.
+                         Pixel ids and ray directions stay frame-global, so N row tiles
+                         concatenate to exactly the 1-GPU frame. */
+  uint32_t flags;
+} rt_config;
+
+/* Defaults of the reference at HEAD: 1024x1024, aa 2, 10 shadow samples, 10 bounces, device 0. */
+void rt_default_config(rt_config *cfg);
+
+/* Replaces selectOpenCLDevice + context/queue/program/kernel/buffer creation
+ * (skeleton.cpp:374-446).  Returns NULL on failure; rt_last_error(NULL) then
+ * holds the reason. */
+rt_ctx *rt_create(const rt_config *cfg);
+
+/* Replaces the scene flatten + three blocking clEnqueueWriteBuffer calls
+ * (skeleton.cpp:474-496).  verts_xyzw: 3n float4 (v0,v1,v2 per triangle, w
+ * ignored); normals_xyzw: n float4; colors_rgbm: n float4 with w = material
+ * (>0 diffuse, 0 mirror, <0 glass; -1 casts no shadow).  Triangle order is
+ * significant (lowest index wins exact ties, kernels.cl:120).  May be called
+ * again to replace the scene. */
+int rt_upload_scene(rt_ctx *ctx, const float *verts_xyzw, const float *normals_xyzw,
+                    const float *colors_rgbm, int n_triangles);
+
+/* Replaces offload_rendering (skeleton.cpp:146-182): rotation-matrix upload,
+ * the four per-frame kernel arguments, the NDRange launch and the BLOCKING
+ * read-back.  rot12 = three rows with float4 stride (:149-151); cam/light =
+ * the 16 bytes the reference passes as float3 (w ignored, :162-165).
+ * host_argb receives rows [row0,row0+rows) only: rows*width uint32 ARGB8888
+ * (kernels.cl:37-40), i.e. the whole frame for an untiled context.  The frame
+ * is valid on return. */
+int rt_render(rt_ctx *ctx, const float rot12[12], const float cam[4], const float light[4],
+              float focal_length, uint32_t *host_argb);
+
+/* Kernel only, asynchronous, no read-back.  dev_argb: device pointer to the
+ * WHOLE frame (width*height uint32) — this context's tile is written at row
+ * offset row0; NULL = the context's own frame buffer (rt_device_frame).  May
+ * be a peer-mapped pointer of another GPU (NVLink store path).  stream: a
+ * cudaStream_t, or NULL for the context's stream.  Timing of the last launch:
+ * rt_last_kernel_ms (synchronises). */
+int rt_render_device(rt_ctx *ctx, const float rot12[12], const float cam[4], const float light[4],
+                     float focal_length, uint32_t *dev_argb, void *stream);
+
+/* Wait for everything queued on the context's stream. */
+int rt_synchronize(rt_ctx *ctx);
+
+/* Device pointer of the context's own whole-frame buffer (width*height uint32). */
+uint32_t *rt_device_frame(rt_ctx *ctx);
+
+/* Milliseconds (CUDA events on the launching stream) of the last render launch
+ * made by rt_render / rt_render_device; < 0 on error. */
+float rt_last_kernel_ms(rt_ctx *ctx);
+
+/* Number of kernels launched by this context so far. */
+uint64_t rt_kernel_launches(const rt_ctx *ctx);
+
+/* "brute" or "bvh": which traversal rt_upload_scene selected. */
+const char *rt_scene_mode(const rt_ctx *ctx);
+
+/* The reference never releases anything (no clRelease* anywhere); this does. */
+void rt_destroy(rt_ctx *ctx);
+
+/* Last error message of ctx (or of rt_create when ctx == NULL). Never NULL. */
+const char *rt_last_error(const rt_ctx *ctx);
+
+/* Library version string, e.g. "uob_rt 0.1 (sm_100a)". */
+const char *rt_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* UOB_RT_H */

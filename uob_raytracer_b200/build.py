@@ -1,0 +1,74 @@
+"""Build the in-tree native library uob_raytracer_b200/libuob_rt.so with nvcc for sm_100a.
+
+nvcc cross-compiles without a GPU; the .so travels to the GPU box with the repo
+snapshot (it is git-ignored, not gpurun-ignored).
+"""
+from __future__ import annotations
+
+import os
+import subprocess
+import sys
+
+PKG = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(PKG, "csrc")
+LIB = os.path.join(PKG, "libuob_rt.so")
+HOST_LIB = os.path.join(PKG, "libuob_host.so")
+HOST_SOURCES = [os.path.join("host", "uob_host.cpp")]
+HOST_FLAGS = ["-std=c++17", "-O2", "-ffp-contract=off", "-fno-fast-math", "-fPIC", "-shared", "-Wall"]
+
+SOURCES = ["rt_api.cu", "rt_draw.cu"]
+NVCC_FLAGS = [
+    "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
+    "-Xcompiler", "-fPIC,-ffp-contract=off,-fno-fast-math", "--expt-relaxed-constexpr",
+]
+
+
+def _nvcc() -> str:
+    for cand in (os.environ.get("NVCC"), "/usr/local/cuda/bin/nvcc", "nvcc"):
+        if cand and (os.path.sep not in cand or os.path.exists(cand)):
+            return cand
+    return "nvcc"
+
+
+def needs_build() -> bool:
+    if not os.path.exists(LIB):
+        return True
+    t = os.path.getmtime(LIB)
+    for root, _, files in os.walk(CSRC):
+        for f in files:
+            if os.path.getmtime(os.path.join(root, f)) > t:
+                return True
+    inc = os.path.join(PKG, "..", "include", "uob_rt.h")
+    return os.path.getmtime(inc) > t
+
+
+def build_host(force: bool = False) -> str:
+    """libuob_host.so: scene sources, camera/light state, framebuffer dump (plain g++)."""
+    srcs = [os.path.join(CSRC, s) for s in HOST_SOURCES]
+    if not force and os.path.exists(HOST_LIB) and all(os.path.getmtime(s) < os.path.getmtime(HOST_LIB) for s in srcs):
+        return HOST_LIB
+    subprocess.check_call(["g++", *HOST_FLAGS, *srcs, "-o", HOST_LIB])
+    return HOST_LIB
+
+
+def build(force: bool = False, verbose: bool = False) -> str:
+    build_host(force)
+    if not force and not needs_build():
+        return LIB
+    objs = []
+    os.makedirs(os.path.join(PKG, "build"), exist_ok=True)
+    for src in SOURCES:
+        obj = os.path.join(PKG, "build", src.replace(".cu", ".o"))
+        cmd = [_nvcc(), *NVCC_FLAGS, "-c", os.path.join(CSRC, src), "-o", obj]
+        if verbose:
+            cmd.insert(1, "-Xptxas=-v")
+            print(" ".join(cmd), file=sys.stderr)
+        subprocess.check_call(cmd)
+        objs.append(obj)
+    cmd = [_nvcc(), "-Wno-deprecated-gpu-targets", "-shared", "-o", LIB, *objs, "-lcudart"]
+    subprocess.check_call(cmd)
+    return LIB
+
+
+if __name__ == "__main__":
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))

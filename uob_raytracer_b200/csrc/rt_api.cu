@@ -1,0 +1,253 @@
+// rt_api.cu — implementation of the C ABI in include/uob_rt.h.
+#include <math.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "rt_internal.h"
+#include "rt_types.h"
+
+static thread_local std::string g_create_err;
+
+#define RT_CUDA(ctx, call, what)                                                                    \
+  do {                                                                                              \
+    cudaError_t e_ = (call);                                                                        \
+    if (e_ != cudaSuccess) {                                                                        \
+      char buf_[512];                                                                               \
+      snprintf(buf_, sizeof buf_, "CUDA error during '%s': %s (%d)", what, cudaGetErrorString(e_), (int)e_); \
+      (ctx)->err = buf_;                                                                            \
+      return RT_ERR_CUDA;                                                                           \
+    }                                                                                               \
+  } while (0)
+
+extern "C" {
+
+const char *rt_version(void) { return "uob_rt 0.1 (sm_100a)"; }
+
+void rt_default_config(rt_config *cfg) {
+  if (!cfg) return;
+  memset(cfg, 0, sizeof *cfg);
+  cfg->width = 1024;   // skeleton.cpp:32-33
+  cfg->height = 1024;
+  cfg->aa = 2;              // kernels.cl:12-14
+  cfg->shadow_samples = 10; // kernels.cl:316
+  cfg->max_bounces = 10;    // kernels.cl:343
+  cfg->device = 0;
+  cfg->row0 = 0;
+  cfg->rows = 0;
+  cfg->flags = 0;
+}
+
+const char *rt_last_error(const rt_ctx *ctx) { return ctx ? ctx->err.c_str() : g_create_err.c_str(); }
+
+static int free_ctx(rt_ctx *ctx) {
+  if (!ctx) return RT_OK;
+  cudaSetDevice(ctx->cfg.device);
+  if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+  if (ctx->d_frame) cudaFree(ctx->d_frame);
+  if (ctx->d_scene) cudaFree(ctx->d_scene);
+  if (ctx->ev0) cudaEventDestroy(ctx->ev0);
+  if (ctx->ev1) cudaEventDestroy(ctx->ev1);
+  if (ctx->stream) cudaStreamDestroy(ctx->stream);
+  delete ctx;
+  return RT_OK;
+}
+
+rt_ctx *rt_create(const rt_config *cfg) {
+  g_create_err.clear();
+  if (!cfg) {
+    g_create_err = "rt_create: cfg is NULL";
+    return nullptr;
+  }
+  if (cfg->width <= 0 || cfg->height <= 0 || cfg->aa < 1 || cfg->aa > 16 || cfg->shadow_samples < 1 || cfg->max_bounces < 0) {
+    g_create_err = "rt_create: width/height must be > 0, 1 <= aa <= 16, shadow_samples >= 1, max_bounces >= 0";
+    return nullptr;
+  }
+  // pixel ids are computed in float and converted to int (kernels.cl:380); keep them representable
+  if ((long long)cfg->width * cfg->height >= (1ll << 31)) {
+    g_create_err = "rt_create: width*height must be < 2^31";
+    return nullptr;
+  }
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0) {
+    g_create_err = std::string("rt_create: no CUDA device (") + cudaGetErrorString(e) + "); there is no CPU fallback";
+    return nullptr;
+  }
+  if (cfg->device < 0 || cfg->device >= ndev) {
+    char buf[128];
+    snprintf(buf, sizeof buf, "device index set to %d but only %d devices available", cfg->device, ndev);  // cf. skeleton.cpp:560-565
+    g_create_err = buf;
+    return nullptr;
+  }
+  rt_ctx *ctx = new rt_ctx();
+  ctx->cfg = *cfg;
+  ctx->row0 = cfg->rows > 0 ? cfg->row0 : 0;
+  ctx->rows = cfg->rows > 0 ? cfg->rows : cfg->height;
+  if (ctx->row0 < 0 || ctx->row0 + ctx->rows > cfg->height) {
+    g_create_err = "rt_create: row tile outside the frame";
+    delete ctx;
+    return nullptr;
+  }
+  auto fail = [&](const char *what, cudaError_t err) -> rt_ctx * {
+    g_create_err = std::string("CUDA error during '") + what + "': " + cudaGetErrorString(err);
+    free_ctx(ctx);
+    return nullptr;
+  };
+  if ((e = cudaSetDevice(cfg->device)) != cudaSuccess) return fail("selecting device", e);
+  cudaDeviceProp prop;
+  if ((e = cudaGetDeviceProperties(&prop, cfg->device)) != cudaSuccess) return fail("querying device", e);
+  ctx->sm_count = prop.multiProcessorCount;
+  if ((e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)) != cudaSuccess) return fail("creating stream", e);
+  if ((e = cudaEventCreate(&ctx->ev0)) != cudaSuccess) return fail("creating event", e);
+  if ((e = cudaEventCreate(&ctx->ev1)) != cudaSuccess) return fail("creating event", e);
+  if ((e = cudaMalloc(&ctx->d_frame, sizeof(uint32_t) * (size_t)cfg->width * cfg->height)) != cudaSuccess)
+    return fail("creating screen buffer", e);
+  if ((e = cudaMemsetAsync(ctx->d_frame, 0, sizeof(uint32_t) * (size_t)cfg->width * cfg->height, ctx->stream)) != cudaSuccess)
+    return fail("clearing screen buffer", e);
+  return ctx;
+}
+
+void rt_destroy(rt_ctx *ctx) { free_ctx(ctx); }
+
+int rt_upload_scene(rt_ctx *ctx, const float *verts, const float *normals, const float *colors, int n) {
+  if (!ctx) return RT_ERR_INVALID;
+  if (!verts || !normals || !colors || n < 0) {
+    ctx->err = "rt_upload_scene: NULL buffer or negative triangle count";
+    return RT_ERR_INVALID;
+  }
+  RT_CUDA(ctx, cudaSetDevice(ctx->cfg.device), "selecting device");
+  // Shadow casters: everything except material == -1 (kernels.cl:247)
+  int n_sh = 0;
+  for (int i = 0; i < n; i++) n_sh += (colors[4 * i + 3] != -1.0f);
+  const size_t smem = rt::brute_smem_bytes(n, n_sh);
+  const bool brute_ok = smem <= rt::brute_smem_limit();
+  bool use_bvh = !brute_ok;
+  if (ctx->cfg.flags & RT_FLAG_FORCE_BVH) use_bvh = true;
+  if ((ctx->cfg.flags & RT_FLAG_FORCE_BRUTE) && !brute_ok) {
+    ctx->err = "rt_upload_scene: scene too large for the brute-force (shared-memory) path";
+    return RT_ERR_INVALID;
+  }
+  if (use_bvh) {
+    ctx->err = "rt_upload_scene: BVH path not built yet";
+    return RT_ERR_INVALID;
+  }
+  // Per-triangle constants, computed with the single-rounded operations the
+  // reference kernel performs per ray (kernels.cl:102-104 and the cofactors of
+  // det, :31-35).  volatile keeps the host compiler from contracting a*b-c*d.
+  std::vector<float4> h(5 * (size_t)n + 3 * (size_t)n_sh);
+  float4 *ta = h.data(), *tb = ta + n, *tc = tb + n, *tn = tc + n, *tcol = tn + n;
+  float4 *sa = tcol + n, *sb = sa + n_sh, *sc = sb + n_sh;
+  int k = 0;
+  for (int i = 0; i < n; i++) {
+    const float *v0 = verts + 12 * (size_t)i, *v1 = v0 + 4, *v2 = v0 + 8;
+    volatile float e1x = v1[0] - v0[0], e1y = v1[1] - v0[1], e1z = v1[2] - v0[2];
+    volatile float e2x = v2[0] - v0[0], e2y = v2[1] - v0[1], e2z = v2[2] - v0[2];
+    volatile float p0 = e1y * e2z, p1 = e1z * e2y, p2 = e1x * e2z, p3 = e1z * e2x, p4 = e1x * e2y, p5 = e1y * e2x;
+    volatile float c0 = p0 - p1, c1 = p2 - p3, c2 = p4 - p5;
+    ta[i] = make_float4(v0[0], v0[1], v0[2], c0);
+    tb[i] = make_float4(e1x, e1y, e1z, c1);
+    tc[i] = make_float4(e2x, e2y, e2z, c2);
+    tn[i] = make_float4(normals[4 * i], normals[4 * i + 1], normals[4 * i + 2], 0.0f);
+    tcol[i] = make_float4(colors[4 * i], colors[4 * i + 1], colors[4 * i + 2], colors[4 * i + 3]);
+    if (colors[4 * i + 3] != -1.0f) {
+      sa[k] = ta[i];
+      sb[k] = tb[i];
+      sc[k] = tc[i];
+      k++;
+    }
+  }
+  if (ctx->d_scene) {
+    RT_CUDA(ctx, cudaStreamSynchronize(ctx->stream), "waiting before scene replacement");
+    RT_CUDA(ctx, cudaFree(ctx->d_scene), "releasing triangle buffer");
+    ctx->d_scene = nullptr;
+  }
+  RT_CUDA(ctx, cudaMalloc(&ctx->d_scene, sizeof(float4) * (h.size() ? h.size() : 1)), "creating triangle buffer");
+  if (!h.empty())
+    RT_CUDA(ctx, cudaMemcpyAsync(ctx->d_scene, h.data(), sizeof(float4) * h.size(), cudaMemcpyHostToDevice, ctx->stream),
+            "writing triangle buffer data");
+  RT_CUDA(ctx, cudaStreamSynchronize(ctx->stream), "writing triangle buffer data");
+  ctx->n = n;
+  ctx->n_sh = n_sh;
+  ctx->use_bvh = use_bvh;
+  ctx->have_scene = true;
+  return RT_OK;
+}
+
+static int render_impl(rt_ctx *ctx, const float rot12[12], const float cam[4], const float light[4], float focal,
+                       uint32_t *dev_argb, cudaStream_t stream) {
+  if (!ctx) return RT_ERR_INVALID;
+  if (!ctx->have_scene) {
+    ctx->err = "rt_render: no scene uploaded";
+    return RT_ERR_NO_SCENE;
+  }
+  if (!rot12 || !cam || !light) {
+    ctx->err = "rt_render: NULL argument";
+    return RT_ERR_INVALID;
+  }
+  RT_CUDA(ctx, cudaSetDevice(ctx->cfg.device), "selecting device");
+  rt::FrameParams fp;
+  fp.W = ctx->cfg.width;
+  fp.H = ctx->cfg.height;
+  fp.row0 = ctx->row0;
+  fp.rows = ctx->rows;
+  fp.A = ctx->cfg.aa;
+  fp.S = ctx->cfg.shadow_samples;
+  fp.B = ctx->cfg.max_bounces;
+  fp.focal = focal;
+  for (int r = 0; r < 3; r++)
+    for (int c = 0; c < 3; c++) fp.rot[3 * r + c] = rot12[4 * r + c];  // float4-strided rows (skeleton.cpp:149-151)
+  for (int c = 0; c < 3; c++) {
+    fp.cam[c] = cam[c];
+    fp.light[c] = light[c];
+  }
+  fp.out = dev_argb ? dev_argb : ctx->d_frame;
+  RT_CUDA(ctx, cudaEventRecord(ctx->ev0, stream), "recording start event");
+  RT_CUDA(ctx, rt::launch_draw_brute(ctx, fp, stream), "enqueueing draw kernel");
+  RT_CUDA(ctx, cudaEventRecord(ctx->ev1, stream), "recording stop event");
+  ctx->timed = true;
+  return RT_OK;
+}
+
+int rt_render_device(rt_ctx *ctx, const float rot12[12], const float cam[4], const float light[4], float focal,
+                     uint32_t *dev_argb, void *stream) {
+  if (!ctx) return RT_ERR_INVALID;
+  return render_impl(ctx, rot12, cam, light, focal, dev_argb, stream ? (cudaStream_t)stream : ctx->stream);
+}
+
+int rt_render(rt_ctx *ctx, const float rot12[12], const float cam[4], const float light[4], float focal, uint32_t *host_argb) {
+  if (!ctx) return RT_ERR_INVALID;
+  if (!host_argb) {
+    ctx->err = "rt_render: host_argb is NULL";
+    return RT_ERR_INVALID;
+  }
+  int rc = render_impl(ctx, rot12, cam, light, focal, nullptr, ctx->stream);
+  if (rc != RT_OK) return rc;
+  const size_t off = (size_t)ctx->row0 * ctx->cfg.width, cnt = (size_t)ctx->rows * ctx->cfg.width;
+  RT_CUDA(ctx, cudaMemcpyAsync(host_argb, ctx->d_frame + off, sizeof(uint32_t) * cnt, cudaMemcpyDeviceToHost, ctx->stream),
+          "reading screen buffer data");
+  RT_CUDA(ctx, cudaStreamSynchronize(ctx->stream), "reading screen buffer data");
+  return RT_OK;
+}
+
+int rt_synchronize(rt_ctx *ctx) {
+  if (!ctx) return RT_ERR_INVALID;
+  RT_CUDA(ctx, cudaSetDevice(ctx->cfg.device), "selecting device");
+  RT_CUDA(ctx, cudaStreamSynchronize(ctx->stream), "waiting for the stream");
+  return RT_OK;
+}
+
+uint32_t *rt_device_frame(rt_ctx *ctx) { return ctx ? ctx->d_frame : nullptr; }
+
+float rt_last_kernel_ms(rt_ctx *ctx) {
+  if (!ctx || !ctx->timed) return -1.0f;
+  if (cudaEventSynchronize(ctx->ev1) != cudaSuccess) return -1.0f;
+  float ms = -1.0f;
+  if (cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1) != cudaSuccess) return -1.0f;
+  return ms;
+}
+
+uint64_t rt_kernel_launches(const rt_ctx *ctx) { return ctx ? ctx->launches : 0; }
+
+const char *rt_scene_mode(const rt_ctx *ctx) { return (ctx && ctx->use_bvh) ? "bvh" : "brute"; }
+
+}  // extern "C"

@@ -1,0 +1,353 @@
+// rt_brute.cuh — brute-force render path (small scenes staged in shared memory).
+//
+// Device equivalents of the helpers of Source/kernels.cl, written once for both
+// arithmetic policies (rt_math.cuh).  What differs from the reference's loop
+// structure, and why it does not change results:
+//   * per-triangle constants (e1 = v1-v0, e2 = v2-v0 and the three cofactors of
+//     the first row of det[., e1, e2]) are precomputed at upload with the same
+//     single-rounded operations the kernel would perform (rt_scene.cu);
+//   * the any-hit loop (in_shadow, kernels.cl:243-311) runs triangle-outer /
+//     shadow-sample-inner: everything that depends only on (start, triangle) —
+//     b, det[b,e1,e2] and the cofactors of det[-d,b,e2], det[-d,e1,b] — is
+//     computed once per triangle instead of once per sample.  in_shadow returns
+//     a boolean OR over occluders, so the order of evaluation is immaterial;
+//   * the fast policy decides t >= 0, |t d|^2 < r^2, u >= 0, v >= 0, u+v <= 1
+//     without dividing (the sign of det A is carried instead).
+#pragma once
+#include "rt_math.cuh"
+#include "rt_types.h"
+
+namespace rt {
+
+// Analytic spheres baked into the reference kernel (kernels.cl:7-10): centre.xyz,
+// radius^2 in .w; colour.w is the material (-1 glass, 0 mirror).
+#define RT_SPHERES 2
+__constant__ float4 c_sphere_center_r2[RT_SPHERES] = {{0.3f, 0.1f, -0.5f, 0.075f}, {-0.4f, 0.8f, -0.5f, 0.05f}};
+__constant__ float4 c_sphere_color[RT_SPHERES] = {{0.0f, 0.0f, 0.0f, -1.0f}, {0.0f, 0.0f, 0.0f, 0.0f}};
+
+#define RT_GLASS 1.52f
+#define RT_AIR 1.0f
+#define RT_BIAS 0.0001f
+#define RT_INDIRECT 0.5f
+#define RT_LIGHT_COLOR 16.0f
+#define RT_LIGHT_SPREAD 0.05f
+#define RT_PI_F 3.14159265358979323846f
+
+// Scene as the kernels read it.  Closest-hit arrays hold all n triangles in
+// upload order; the shadow arrays hold only shadow casters (material != -1,
+// kernels.cl:247), also in upload order.
+//   ta[i] = (v0.xyz, c0)   tb[i] = (e1.xyz, c1)   tc[i] = (e2.xyz, c2)
+//   with c0 = e1.y*e2.z - e1.z*e2.y, c1 = e1.x*e2.z - e1.z*e2.x, c2 = e1.x*e2.y - e1.y*e2.x
+//   so that det[m, e1, e2] = (m.x*c0 - m.y*c1) + m.z*c2   (kernels.cl:31-35)
+struct SceneView {
+  const float4 *ta, *tb, *tc;  // closest-hit triangles
+  const float4 *tn, *tcol;     // normals, colours (w = material)
+  const float4 *sa, *sb, *sc;  // shadow casters
+  int n, n_sh;
+};
+
+template <class T> struct HitRec {
+  int id;  // -1 none, -2 sphere, >=0 triangle (kernels.cl:28)
+  V3<T> point, normal;
+  float4 color;
+};
+
+// ---------------------------------------------------------------------------
+// Closest hit: kernels.cl:92-166 / :168-241.
+// ---------------------------------------------------------------------------
+template <class T>
+__device__ __forceinline__ void closest_hit(const SceneView &sc, V3<T> start, V3<T> dir, HitRec<T> &hit) {
+  T current_t = T(3.402823466e+38f);  // MAXFLOAT
+  const V3<T> nd = -dir;
+  int best = -1;
+  T best_u = T(0.0f), best_v = T(0.0f);
+  for (int i = 0; i < sc.n; i++) {
+    const float4 A = sc.ta[i], Bq = sc.tb[i], C = sc.tc[i];
+    const V3<T> v0 = xyz<T>(A), e1 = xyz<T>(Bq), e2 = xyz<T>(C);
+    const T c0 = T(A.w), c1 = T(Bq.w), c2 = T(C.w);
+    const V3<T> b = start - v0;
+    const T detA = (nd.x * c0 - nd.y * c1) + nd.z * c2;
+    const T inv = rcp_(detA);
+    const T t = ((b.x * c0 - b.y * c1) + b.z * c2) * inv;
+    const T u = ((nd.x * (b.y * e2.z - b.z * e2.y) - nd.y * (b.x * e2.z - b.z * e2.x)) + nd.z * (b.x * e2.y - b.y * e2.x)) * inv;
+    const T v = ((nd.x * (e1.y * b.z - e1.z * b.y) - nd.y * (e1.x * b.z - e1.z * b.x)) + nd.z * (e1.x * b.y - e1.y * b.x)) * inv;
+    if (t < current_t && u >= T(0.0f) && v >= T(0.0f) && (u + v) <= T(1.0f) && t >= T(0.0f)) {
+      best = i;
+      best_u = u;
+      best_v = v;
+      current_t = t;
+    }
+  }
+  if (best >= 0) {
+    // (v0 + u*e1) + v*e2 of the winning triangle — same values as storing at acceptance time
+    const V3<T> v0 = xyz<T>(sc.ta[best]), e1 = xyz<T>(sc.tb[best]), e2 = xyz<T>(sc.tc[best]);
+    hit.id = best;
+    hit.point = (v0 + scale(best_u, e1)) + scale(best_v, e2);
+    hit.normal = xyz<T>(sc.tn[best]);
+    hit.color = sc.tcol[best];
+  }
+#pragma unroll
+  for (int i = 0; i < RT_SPHERES; i++) {
+    const float4 cr = c_sphere_center_r2[i];
+    const V3<T> ctr = xyz<T>(cr);
+    const V3<T> L = start - ctr;
+    const T a = dot(dir, dir);
+    const T b = T(2.0f) * dot(dir, L);
+    const T c = dot(L, L) - T(cr.w);
+    const T disc = b * b - T(4.0f) * a * c;
+    if (disc < T(0.0f)) continue;
+    const T sq = sqrt_(disc);
+    const T q = (b > T(0.0f)) ? T(-0.5f) * (b + sq) : T(-0.5f) * (b - sq);
+    const T x0 = div_(q, a);
+    const T x1 = div_(c, q);
+    const T x_min = cl_min(x0, x1);
+    const T x_max = cl_max(x0, x1);
+    T x;
+    if (x_min >= T(0.0f) && x_min < current_t) x = x_min;
+    else if (x_max >= T(0.0f) && x_max < current_t) x = x_max;
+    else continue;
+    hit.id = -2;
+    hit.point = start + scale(x, dir);
+    hit.normal = normalize(hit.point - ctr);
+    hit.color = c_sphere_color[i];
+    current_t = x;
+  }
+}
+
+// ---------------------------------------------------------------------------
+// Any hit for CH shadow rays sharing one origin: kernels.cl:243-311.
+// Returns a bit mask: bit k set = sample k is in shadow.
+// ---------------------------------------------------------------------------
+template <class T, int CH>
+__device__ __forceinline__ unsigned shadow_chunk(const SceneView &sc, V3<T> start, const V3<T> (&d)[CH], T radius_sq) {
+  unsigned occ = 0u;
+  constexpr unsigned FULL = (CH >= 32) ? 0xffffffffu : ((1u << CH) - 1u);
+  [[maybe_unused]] T dd[CH];  // |d_k|^2 (fast policy)
+  if constexpr (!is_strict<T>::value) {
+#pragma unroll
+    for (int k = 0; k < CH; k++) dd[k] = d[k].x * d[k].x + d[k].y * d[k].y + d[k].z * d[k].z;
+  }
+  for (int i = 0; i < sc.n_sh; i++) {
+    const float4 A = sc.sa[i], Bq = sc.sb[i], C = sc.sc[i];
+    const V3<T> v0 = xyz<T>(A), e1 = xyz<T>(Bq), e2 = xyz<T>(C);
+    const T c0 = T(A.w), c1 = T(Bq.w), c2 = T(C.w);
+    const V3<T> b = start - v0;
+    const T detA0 = (b.x * c0 - b.y * c1) + b.z * c2;
+    // cofactors of det[-d, b, e2] and det[-d, e1, b]: independent of the sample
+    const T U0 = b.y * e2.z - b.z * e2.y, U1 = b.x * e2.z - b.z * e2.x, U2 = b.x * e2.y - b.y * e2.x;
+    const T V0 = e1.y * b.z - e1.z * b.y, V1 = e1.x * b.z - e1.z * b.x, V2 = e1.x * b.y - e1.y * b.x;
+    if constexpr (is_strict<T>::value) {
+#pragma unroll
+      for (int k = 0; k < CH; k++) {
+        if ((occ >> k) & 1u) continue;
+        const V3<T> nd = -d[k];
+        const T detA = (nd.x * c0 - nd.y * c1) + nd.z * c2;
+        const T inv = rcp_(detA);
+        const T t = detA0 * inv;
+        const V3<T> dv = scale(t, d[k]);
+        const T dist = dv.x * dv.x + dv.y * dv.y + dv.z * dv.z;
+        if (t >= T(0.0f) && dist < radius_sq) {
+          const T u = ((nd.x * U0 - nd.y * U1) + nd.z * U2) * inv;
+          const T v = ((nd.x * V0 - nd.y * V1) + nd.z * V2) * inv;
+          if (u >= T(0.0f) && v >= T(0.0f) && (u + v) <= T(1.0f)) occ |= 1u << k;
+        }
+      }
+    } else {
+      const T num2 = detA0 * detA0;
+#pragma unroll
+      for (int k = 0; k < CH; k++) {
+        // den = det[-d, e1, e2];  t = detA0/den
+        const T den = -((d[k].x * c0 - d[k].y * c1) + d[k].z * c2);
+        // t >= 0  and  t^2 |d|^2 < r^2, without dividing (den == 0 fails the second test)
+        const bool s1 = (detA0 * den >= 0.0f) && (num2 * dd[k] < radius_sq * (den * den));
+        if (s1) {
+          const T sg = (den < 0.0f) ? -1.0f : 1.0f;
+          const T D1 = -((d[k].x * U0 - d[k].y * U1) + d[k].z * U2) * sg;  // u * |den|
+          const T D2 = -((d[k].x * V0 - d[k].y * V1) + d[k].z * V2) * sg;  // v * |den|
+          if (D1 >= 0.0f && D2 >= 0.0f && (D1 + D2) <= den * sg) occ |= 1u << k;
+        }
+      }
+    }
+    if (occ == FULL) return occ;
+  }
+#pragma unroll
+  for (int i = 0; i < RT_SPHERES; i++) {
+    if (c_sphere_color[i].w == -1.0f) continue;  // glass casts no shadow (kernels.cl:279)
+    const float4 cr = c_sphere_center_r2[i];
+    const V3<T> L = start - xyz<T>(cr);
+    const T c = dot(L, L) - T(cr.w);
+#pragma unroll
+    for (int k = 0; k < CH; k++) {
+      if ((occ >> k) & 1u) continue;
+      const T a = dot(d[k], d[k]);
+      const T b = T(2.0f) * dot(d[k], L);
+      const T disc = b * b - T(4.0f) * a * c;
+      if (disc < T(0.0f)) continue;
+      T x0, x1;
+      if constexpr (is_strict<T>::value) {
+        const T sq = sqrt_(disc);
+        const T q = (b > T(0.0f)) ? T(-0.5f) * (b + sq) : T(-0.5f) * (b - sq);
+        x0 = div_(q, a);
+        x1 = div_(c, q);
+      } else {
+        const float sq = sqrt_approx(disc);
+        const float q = (b > 0.0f) ? -0.5f * (b + sq) : -0.5f * (b - sq);
+        x0 = q * rcp_approx(a);
+        x1 = c * rcp_approx(q);
+      }
+      const T x_min = cl_min(x0, x1);
+      const T x_max = cl_max(x0, x1);
+      const V3<T> min_dir = scale(x_min, d[k]);
+      const V3<T> max_dir = scale(x_max, d[k]);
+      const T min_dist = dot(min_dir, min_dir);
+      const T max_dist = dot(max_dir, max_dir);
+      if ((x_min >= T(0.0f) && min_dist < radius_sq) || (x_max >= T(0.0f) && max_dist < radius_sq)) occ |= 1u << k;
+    }
+  }
+  return occ;
+}
+
+// ---------------------------------------------------------------------------
+// direct_light: kernels.cl:313-340.  The jitter sequence depends on the pixel
+// id only (same S jitters for every AA sample and bounce of a pixel).
+// ---------------------------------------------------------------------------
+template <class T, int CH>
+__device__ __forceinline__ V3<T> direct_light(const SceneView &sc, V3<T> point, V3<T> normal, V3<T> light_pos, int S,
+                                              int global_id) {
+  // (uint3)(global_id, global_id*91.0f, global_id*19.0f) then one xorshift (kernels.cl:319)
+  uint32_t rx = xorshift32((uint32_t)global_id);
+  uint32_t ry = xorshift32(__float2uint_rz(__fmul_rn(__int2float_rn(global_id), 91.0f)));
+  uint32_t rz = xorshift32(__float2uint_rz(__fmul_rn(__int2float_rn(global_id), 19.0f)));
+  const V3<T> dir = light_pos - point;
+  const V3<T> start = point + scale(T(RT_BIAS), dir);
+  const T radius_sq = (dir.x * dir.x + dir.y * dir.y) + dir.z * dir.z;
+  const T lam = T(RT_LIGHT_COLOR) * cl_max(dot(dir, normal), T(0.0f));
+  const T den = T(4.0f) * T(RT_PI_F) * radius_sq;
+  T total = T(0.0f);
+  [[maybe_unused]] int lit = 0;
+  for (int s0 = 0; s0 < S; s0 += CH) {
+    V3<T> d[CH];
+#pragma unroll
+    for (int k = 0; k < CH; k++) {
+      rx = xorshift32(rx);
+      ry = xorshift32(ry);
+      rz = xorshift32(rz);
+      d[k] = dir + V3<T>(crush1<T>(rx, RT_LIGHT_SPREAD), crush1<T>(ry, RT_LIGHT_SPREAD), crush1<T>(rz, RT_LIGHT_SPREAD));
+    }
+    unsigned occ = shadow_chunk<T, CH>(sc, start, d, radius_sq);
+    if (s0 + CH > S) occ |= ~0u << (S - s0);  // ragged last chunk: ignore the padding samples
+    if constexpr (is_strict<T>::value) {
+#pragma unroll
+      for (int k = 0; k < CH; k++) {
+        if (s0 + k < S) {
+          const T mask = ((occ >> k) & 1u) ? T(0.0f) : T(1.0f);
+          total = total + div_(mask * lam, den);
+        }
+      }
+    } else {
+      lit += CH - __popc(occ & ((CH >= 32) ? 0xffffffffu : ((1u << CH) - 1u)));
+    }
+  }
+  if constexpr (is_strict<T>::value) {
+    const T r = div_(total, T(__int2float_rn(S)));
+    return V3<T>(r, r, r);
+  } else {
+    const float r = (float)lit * lam * rcp_approx(den * (float)S);
+    return V3<T>(r, r, r);
+  }
+}
+
+// kernels.cl:54-65
+template <class T>
+__device__ __forceinline__ void reflect_ray(V3<T> dir, V3<T> normal, V3<T> point, V3<T> &o_start, V3<T> &o_dir, float &o_medium) {
+  const T dn = dot(dir, normal);
+  const V3<T> r = dir - scale(T(2.0f), scale(dn, normal));
+  o_start = point + scale(T(RT_BIAS), r);
+  o_medium = RT_AIR;
+  o_dir = normalize(r);
+}
+
+// kernels.cl:67-88 (TIR branch is dead code: sqrt(<0) is NaN, NaN<0 is false; the
+// NaN ray then hits nothing and the sample is black)
+template <class T>
+__device__ __forceinline__ void refract_ray(V3<T> dir, V3<T> normal, V3<T> point, float medium, V3<T> &o_start, V3<T> &o_dir,
+                                            float &o_medium) {
+  const bool air = (medium == RT_AIR);
+  const T n1 = air ? T(RT_AIR) : T(RT_GLASS);
+  const T n2 = air ? T(RT_GLASS) : T(RT_AIR);
+  T c1 = dot(normal, dir);
+  if (c1 < T(0.0f)) normal = scale(T(-1.0f), normal);
+  c1 = abs_(c1);
+  const T n = div_(n1, n2);
+  const T c2 = sqrt_(T(1.0f) - (n * n) * (T(1.0f) - (c1 * c1)));
+  const V3<T> r = scale(n, dir) + scale(n * c1 - c2, -normal);
+  o_start = point + scale(T(RT_BIAS), r);
+  o_medium = raw(n2);
+  o_dir = normalize(r);
+}
+
+// secondary_light: kernels.cl:342-365
+template <class T, int CH>
+__device__ __forceinline__ V3<T> secondary_light(const SceneView &sc, V3<T> dir, HitRec<T> hit, V3<T> light_pos, int S, int B,
+                                                 int global_id) {
+  float medium = RT_AIR;
+  for (int b = 0; b < B && hit.color.w <= 0.0f; b++) {
+    V3<T> start, ndir;
+    if (hit.color.w == 0.0f) reflect_ray<T>(dir, hit.normal, hit.point, start, ndir, medium);
+    else refract_ray<T>(dir, hit.normal, hit.point, medium, start, ndir, medium);
+    dir = ndir;
+    hit.id = -1;
+    hit.color.w = 1.0f;
+    closest_hit<T>(sc, start, dir, hit);
+    if (hit.id != -1 && hit.color.w > 0.0f) {
+      const V3<T> dl = direct_light<T, CH>(sc, hit.point, hit.normal, light_pos, S, global_id);
+      const V3<T> light(T(RT_INDIRECT) + dl.x, T(RT_INDIRECT) + dl.y, T(RT_INDIRECT) + dl.z);
+      return scale(T(0.9f), light) * xyz<T>(hit.color);
+    }
+  }
+  return V3<T>(T(0.0f), T(0.0f), T(0.0f));
+}
+
+// kernels.cl:37-40
+template <class T> __device__ __forceinline__ uint32_t pack_argb(V3<T> c) {
+  const uint32_t r = __float2uint_rz(raw(cl_min(cl_max(T(255.0f) * c.x, T(0.f)), T(255.f))));
+  const uint32_t g = __float2uint_rz(raw(cl_min(cl_max(T(255.0f) * c.y, T(0.f)), T(255.f))));
+  const uint32_t b = __float2uint_rz(raw(cl_min(cl_max(T(255.0f) * c.z, T(0.f)), T(255.f))));
+  return (255u << 24) + (r << 16) + (g << 8) + b;
+}
+
+// One pixel of `draw` (kernels.cl:368-428).
+template <class T, int CH>
+__device__ __forceinline__ uint32_t shade_pixel(const SceneView &sc, const FrameParams &p, int x, int y) {
+  const T SW = T(__int2float_rn(p.W)), SH = T(__int2float_rn(p.H));
+  const int A = p.A;
+  const T fA = T(__int2float_rn(A));
+  // const int global_id = y*SCREEN_WIDTH + x  in float arithmetic (kernels.cl:380)
+  const int global_id = __float2int_rz(raw(T(__int2float_rn(y)) * SW + T(__int2float_rn(x))));
+  const V3<T> base(T(__int2float_rn(x * A)) - div_(SW * fA, T(2.0f)), T(__int2float_rn(y * A)) - div_(SH * fA, T(2.0f)), T(p.focal));
+  const V3<T> r0(T(p.rot[0]), T(p.rot[1]), T(p.rot[2])), r1(T(p.rot[3]), T(p.rot[4]), T(p.rot[5])), r2(T(p.rot[6]), T(p.rot[7]), T(p.rot[8]));
+  const V3<T> cam(T(p.cam[0]), T(p.cam[1]), T(p.cam[2])), light(T(p.light[0]), T(p.light[1]), T(p.light[2]));
+  V3<T> total(T(0.0f), T(0.0f), T(0.0f));
+  for (int dy = 0; dy < A; dy++) {
+    for (int dx = 0; dx < A; dx++) {
+      const V3<T> d0 = base + V3<T>(T(__int2float_rn(dx)), T(__int2float_rn(dy)), T(0.0f));
+      const V3<T> dir = normalize(V3<T>(dot(r0, d0), dot(r1, d0), dot(r2, d0)));
+      HitRec<T> hit;
+      hit.id = -1;
+      hit.color = make_float4(0.0f, 0.0f, 0.0f, 1.0f);
+      closest_hit<T>(sc, cam, dir, hit);
+      if (hit.id != -1) {
+        if (hit.color.w <= 0.0f) {
+          total = total + secondary_light<T, CH>(sc, dir, hit, light, p.S, p.B, global_id);
+        } else {
+          const V3<T> fl = direct_light<T, CH>(sc, hit.point, hit.normal, light, p.S, global_id);
+          total = total + xyz<T>(hit.color) * V3<T>(T(RT_INDIRECT) + fl.x, T(RT_INDIRECT) + fl.y, T(RT_INDIRECT) + fl.z);
+        }
+      }
+    }
+  }
+  const T fa = T(__int2float_rn(A * A));
+  return pack_argb<T>(V3<T>(div_(total.x, fa), div_(total.y, fa), div_(total.z, fa)));
+}
+
+}  // namespace rt

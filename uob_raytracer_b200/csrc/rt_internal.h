@@ -1,0 +1,39 @@
+// rt_internal.h — context object behind the C ABI (include/uob_rt.h).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/uob_rt.h"
+
+namespace rt {
+struct FrameParams;
+}
+
+struct rt_ctx {
+  rt_config cfg{};
+  int row0 = 0, rows = 0;  // resolved tile
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  bool timed = false;
+  uint32_t *d_frame = nullptr;  // whole frame, W*H
+  // Brute-force scene: one float4 buffer, [ta|tb|tc|tn|tcol] x n then [sa|sb|sc] x n_sh
+  float4 *d_scene = nullptr;
+  int n = 0, n_sh = 0;
+  bool have_scene = false;
+  bool use_bvh = false;
+  int sm_count = 0;
+  uint64_t launches = 0;
+  std::string err;
+};
+
+namespace rt {
+
+// rt_draw.cu
+cudaError_t launch_draw_brute(rt_ctx *ctx, const FrameParams &fp, cudaStream_t stream);
+size_t brute_smem_bytes(int n, int n_sh);
+size_t brute_smem_limit();
+
+}  // namespace rt

@@ -1,0 +1,21 @@
+// rt_types.h — plain structs shared by the C-ABI layer and the kernels.
+#pragma once
+#include <stdint.h>
+
+namespace rt {
+
+// Per-launch arguments of `draw`: what the reference passes as kernel args 4-8
+// (kernels.cl:368-371; skeleton.cpp:160-167) plus the run-time versions of its
+// compile-time constants and the row tile of this launch.
+struct FrameParams {
+  int W, H;        // whole frame
+  int row0, rows;  // rows rendered by this launch
+  int A, S, B;     // AA edge, shadow samples, max bounces
+  float focal;
+  float rot[9];    // rows r0, r1, r2 (skeleton.cpp:149-151)
+  float cam[3], light[3];
+  uint32_t *out;   // whole-frame ARGB buffer (may be a peer pointer)
+};
+
+
+}  // namespace rt

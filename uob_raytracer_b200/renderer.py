@@ -1,0 +1,119 @@
+"""Python mirror of the reference's device boundary over the C ABI (include/uob_rt.h).
+
+    Renderer(...)            ~ opencl_initialise   (skeleton.cpp:366-497)
+    Renderer.upload_scene    ~ the flatten + three buffer writes (:474-496)
+    Renderer.render          ~ offload_rendering   (:146-182): blocking, frame valid on return
+    Renderer.render_device   ~ kernel only (no read-back), for device-side timing / multi-GPU
+
+Everything executes in libuob_rt.so (CUDA, sm_100a).  No fallback.
+"""
+from __future__ import annotations
+
+import ctypes
+
+import numpy as np
+
+from ._lib import (RT_FLAG_FORCE_BRUTE, RT_FLAG_FORCE_BVH, RT_FLAG_STRICT_IEEE, RT_OK, RtConfig, c_float_p, rt_lib)
+from .host import Camera, Scene
+
+
+class RtError(RuntimeError):
+    pass
+
+
+def _f32(a, n: int) -> np.ndarray:
+    a = np.ascontiguousarray(a, np.float32).reshape(-1)
+    if a.size < n:
+        raise ValueError(f"expected at least {n} floats, got {a.size}")
+    return a
+
+
+class Renderer:
+    def __init__(self, width: int = 1024, height: int = 1024, aa: int = 2, shadow_samples: int = 10,
+                 max_bounces: int = 10, device: int = 0, row0: int = 0, rows: int = 0, strict: bool = False,
+                 force_bvh: bool = False, force_brute: bool = False):
+        self._lib = rt_lib()
+        flags = (RT_FLAG_STRICT_IEEE if strict else 0) | (RT_FLAG_FORCE_BVH if force_bvh else 0) | \
+                (RT_FLAG_FORCE_BRUTE if force_brute else 0)
+        self.cfg = RtConfig(width, height, aa, shadow_samples, max_bounces, device, row0, rows, flags)
+        self._ctx = self._lib.rt_create(ctypes.byref(self.cfg))
+        if not self._ctx:
+            raise RtError(self._lib.rt_last_error(None).decode())
+        self.width, self.height = width, height
+        self.row0 = row0 if rows > 0 else 0
+        self.rows = rows if rows > 0 else height
+
+    # -- lifetime ------------------------------------------------------------
+    def close(self) -> None:
+        if getattr(self, "_ctx", None):
+            self._lib.rt_destroy(self._ctx)
+            self._ctx = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    def _check(self, rc: int) -> None:
+        if rc != RT_OK:
+            raise RtError(f"[{rc}] " + self._lib.rt_last_error(self._ctx).decode())
+
+    # -- scene ---------------------------------------------------------------
+    def upload_scene(self, scene: Scene) -> None:
+        n = scene.n
+        v, nr, c = _f32(scene.verts, 12 * n), _f32(scene.normals, 4 * n), _f32(scene.colors, 4 * n)
+        self._check(self._lib.rt_upload_scene(self._ctx, v.ctypes.data_as(c_float_p), nr.ctypes.data_as(c_float_p),
+                                              c.ctypes.data_as(c_float_p), n))
+
+    @property
+    def scene_mode(self) -> str:
+        return self._lib.rt_scene_mode(self._ctx).decode()
+
+    # -- rendering -----------------------------------------------------------
+    def render(self, rot12, cam, light, focal: float, out: np.ndarray | None = None) -> np.ndarray:
+        """Blocking render + read-back of this context's rows. Returns uint32 [rows, width]."""
+        if out is None:
+            out = np.empty((self.rows, self.width), np.uint32)
+        assert out.dtype == np.uint32 and out.flags.c_contiguous and out.size == self.rows * self.width
+        r, c, l = _f32(rot12, 12), _f32(cam, 3), _f32(light, 3)
+        c4, l4 = np.zeros(4, np.float32), np.zeros(4, np.float32)
+        c4[:3], l4[:3] = c[:3], l[:3]
+        self._check(self._lib.rt_render(self._ctx, r.ctypes.data_as(c_float_p), c4.ctypes.data_as(c_float_p),
+                                        l4.ctypes.data_as(c_float_p), focal, out.ctypes.data))
+        return out
+
+    def render_camera(self, camera: Camera, out: np.ndarray | None = None) -> np.ndarray:
+        return self.render(camera.rot(), camera.position, camera.light, camera.focal, out)
+
+    def render_host_ptr(self, rot12, cam4, light4, focal: float, host_ptr: int) -> None:
+        """Blocking render into a raw host pointer (e.g. pinned memory owned by the caller)."""
+        self._check(self._lib.rt_render(self._ctx, rot12.ctypes.data_as(c_float_p), cam4.ctypes.data_as(c_float_p),
+                                        light4.ctypes.data_as(c_float_p), focal, host_ptr))
+
+    def render_device(self, rot12, cam4, light4, focal: float, dev_ptr: int = 0, stream: int = 0) -> None:
+        """Asynchronous kernel launch only; dev_ptr = whole-frame device buffer (0 = the context's own)."""
+        self._check(self._lib.rt_render_device(self._ctx, rot12.ctypes.data_as(c_float_p),
+                                               cam4.ctypes.data_as(c_float_p), light4.ctypes.data_as(c_float_p), focal,
+                                               dev_ptr or None, stream or None))
+
+    def synchronize(self) -> None:
+        self._check(self._lib.rt_synchronize(self._ctx))
+
+    @property
+    def device_frame_ptr(self) -> int:
+        return int(self._lib.rt_device_frame(self._ctx) or 0)
+
+    @property
+    def last_kernel_ms(self) -> float:
+        return float(self._lib.rt_last_kernel_ms(self._ctx))
+
+    @property
+    def kernel_launches(self) -> int:
+        return int(self._lib.rt_kernel_launches(self._ctx))
