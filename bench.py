@@ -1,0 +1,360 @@
+#!/usr/bin/env python3
+"""bench.py — headline benchmark of the render path.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload cfg2]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+A step is one frame of the workload (default cfg2 of BASELINE.json: Cornell Box 1920x1080, 2x2 AA,
+8-sample soft shadows, <=10 mirror/glass bounces) rendered through libuob_rt.so.  Rays per frame
+are the ORACLE's deterministic counters for that config (tests/golden/ray_counts.json,
+SURVEY.md §8d), never a GPU-side count.
+
+  value        Mrays/s, device time (CUDA events on the launching stream, max over ranks); the
+               scene is resident in HBM, the frame stays on the device.
+  e2e          the same metric through the reference-facing call rt_render (offload_rendering
+               semantics: per-frame arguments, kernel, BLOCKING read-back of the frame into pinned
+               host memory), host wall clock.
+  roofline     dominant kernel (draw_brute) vs the FP32 non-tensor pipe: algorithmic FLOPs per
+               frame (37*T_c + 17*T_s1 + 22*T_s2 + 31*T_sph from the oracle's test
+               counters) / measured kernel time, against an FFMA microbenchmark run just before.
+  cpu_baseline the reference's own kernels.cl compiled for the host (oracle/_ref, kind
+               "reference"; falls back to the C restatement, kind "port") on all host cores.
+
+N > 1: the frame is split into N contiguous row tiles (one per rank, one process per GPU); every
+step ends with an in-place NCCL all-gather of the tiles into the whole frame on every rank
+(strong scaling: the frame is fixed).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+METRIC = "Mrays/sec (Cornell Box 1080p, AA+soft shadows)"
+UNIT = "Mrays/s"
+
+
+def load_counts(workload: str) -> dict:
+    with open(os.path.join(ROOT, "tests", "golden", "ray_counts.json")) as f:
+        return json.load(f)[workload]
+
+
+def algorithmic_flops(c: dict) -> float:
+    """minimal-operation form of the reference's brute-force algorithm, FMA = 2."""
+    return 37.0 * c["closest_tri_tests"] + 17.0 * c["shadow_stage1_tests"] + 22.0 * c["shadow_stage2_tests"] + \
+        31.0 * c["sphere_tests"]
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-i", str(self.index), "-lms", "50"], stdout=subprocess.PIPE, text=True)
+            self.thread = threading.Thread(target=self._pump, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self) -> dict:
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.06)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons, power = [], [], set(), []
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            parts = [p.strip() for p in ln.split(",")]
+            if len(parts) < 7:
+                continue
+            try:
+                sm.append(float(parts[0]))
+                mx.append(float(parts[1]))
+                power.append(float(parts[2]))
+            except ValueError:
+                continue
+            for nm, val in zip(names, parts[3:7]):
+                if val.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "power_w_max": max(power) if power else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def scene_and_camera():
+    import uob_raytracer_b200 as u
+    scene = u.load_test_model()
+    cam = u.Camera()
+    return scene, cam.rot(), cam.position.copy(), cam.light.copy()
+
+
+def cpu_reference_frame(cfg, rows_step: int, threads: int = 0):
+    """One (possibly row-subsampled) frame by the reference's own kernel on host threads.
+    Returns (seconds, rays traced, kind)."""
+    from oracle import bind as ob
+    import uob_raytracer_b200 as u
+    scene, rot, cam4, light4 = scene_and_camera()
+    counts = load_counts(cfg.name)
+    if rows_step == 1:
+        rays = counts["rays"]
+    else:
+        rr = counts.get("row_rays")
+        rays = int(sum(rr[::rows_step])) if rr else counts["rays"] / rows_step
+    t0 = time.perf_counter()
+    if ob.ref_available(cfg.aa, cfg.shadow_samples, cfg.max_bounces):
+        kind = "reference"
+        ob.ref_render(cfg.width, cfg.height, cfg.aa, cfg.shadow_samples, cfg.max_bounces, cfg.focal, scene.verts,
+                      scene.normals, scene.colors, rot, cam4, light4, row_step=rows_step, threads=threads)
+    else:
+        kind = "port"
+        ob.oracle_render(cfg.width, cfg.height, cfg.aa, cfg.shadow_samples, cfg.max_bounces, cfg.focal, scene.verts,
+                         scene.normals, scene.colors, rot, cam4, light4, row_step=rows_step, threads=threads)
+    return time.perf_counter() - t0, rays, kind
+
+
+def pick_row_step(cfg) -> int:
+    """Bound the CPU sample: a full frame when it takes < ~3 s on this host, else every k-th row."""
+    t, _, _ = cpu_reference_frame(cfg, 16)
+    full = t * 16
+    step = 1
+    while full / step > 3.0 and step < 64:
+        step *= 2
+    return step
+
+
+def run_reference(args, cfg) -> int:
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    cores = os.cpu_count() or 1
+    step = pick_row_step(cfg)
+    for _ in range(max(args.warmup, 1)):
+        cpu_reference_frame(cfg, step)
+    total_t, total_rays, kind = 0.0, 0, "reference"
+    for _ in range(args.steps):
+        t, rays, kind = cpu_reference_frame(cfg, step)
+        total_t += t
+        total_rays += rays
+    value = total_rays / total_t / 1e6
+    sample = (f"{args.steps} frames of {cfg.name}, " + ("all rows" if step == 1 else f"every {step}th row") +
+              f" ({total_rays / args.steps:.0f} rays per step), verbatim kernels.cl via g++ shim, -O2 strict IEEE")
+    line = {"impl": "reference", "metric": METRIC, "value": round(value, 3), "unit": UNIT, "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(total_t / args.steps * 1e3, 3),
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": cfg.name, "description": cfg.description, "width": cfg.width, "height": cfg.height,
+                       "aa": cfg.aa, "shadow_samples": cfg.shadow_samples, "max_bounces": cfg.max_bounces},
+            "cpu_baseline": {"value": round(value, 3), "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
+            "e2e": {"value": round(value, 3), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+def run_ours(args, cfg) -> int:
+    import torch
+    import uob_raytracer_b200 as u
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device — the render path has no CPU fallback")
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            raise SystemExit("bench.py: --gpus N > 1 must be launched with torch.distributed.run (one rank per GPU)")
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    W, H = cfg.width, cfg.height
+    if H % world:
+        raise SystemExit(f"height {H} not divisible by {world} ranks")
+    rows = H // world
+    row0 = rank * rows
+    counts = load_counts(cfg.name)
+    scene, rot, cam4, light4 = scene_and_camera()
+
+    r = u.Renderer(W, H, cfg.aa, cfg.shadow_samples, cfg.max_bounces, device=local_rank, row0=row0, rows=rows)
+    r.upload_scene(scene)
+    frame = torch.zeros(H * W, dtype=torch.int32, device=f"cuda:{local_rank}")
+    tile = frame[row0 * W:(row0 + rows) * W]
+    host = torch.empty(H * W, dtype=torch.int32).pin_memory()
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=f"cuda:{local_rank}")  # > 126 MB L2
+    stream = torch.cuda.Stream(device=local_rank)  # a real (non-default) stream: the C ABI launches on it
+    torch.cuda.set_stream(stream)
+    sptr = stream.cuda_stream
+    assert sptr != 0
+
+    def step_device():
+        r.render_device(rot, cam4, light4, cfg.focal, dev_ptr=frame.data_ptr(), stream=sptr)
+        if dist is not None:
+            dist.all_gather_into_tensor(frame, tile)
+
+    fp32_peak = r.measure_fp32_peak() if rank == 0 else 0.0
+
+    # ---- device-timed throughput ------------------------------------------------
+    for _ in range(max(args.warmup, 3)):
+        step_device()
+    torch.cuda.synchronize()
+    if dist is not None:
+        dist.barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    launches0 = r.kernel_launches
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+          for _ in range(args.steps)]
+    torch.cuda.synchronize()
+    t_wall0 = time.perf_counter()
+    for a, k, b in ev:
+        flush.zero_()  # L2 flush between timed iterations; outside the event pair
+        a.record(stream)
+        r.render_device(rot, cam4, light4, cfg.focal, dev_ptr=frame.data_ptr(), stream=sptr)
+        k.record(stream)
+        if dist is not None:
+            dist.all_gather_into_tensor(frame, tile)
+        b.record(stream)
+    torch.cuda.synchronize()
+    t_wall = time.perf_counter() - t_wall0
+    launches = r.kernel_launches - launches0
+    if dist is not None:
+        dist.barrier()
+    step_ms = [a.elapsed_time(b) for a, _, b in ev]
+    kern_ms = [a.elapsed_time(k) for a, k, _ in ev]
+    total_ms = torch.tensor([sum(step_ms), sum(kern_ms)], dtype=torch.float64, device=f"cuda:{local_rank}")
+    if dist is not None:
+        dist.all_reduce(total_ms, op=dist.ReduceOp.MAX)
+    total_step_ms, total_kern_ms = (float(x) for x in total_ms.cpu())
+    clocks = sampler.stop() if rank == 0 else {}
+
+    # ---- end to end through rt_render (host buffers) ------------------------------
+    e2e_line = None
+    if world == 1:
+        hp = host.data_ptr()
+        for _ in range(3):
+            r.render_host_ptr(rot, cam4, light4, cfg.focal, hp)
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            r.render_host_ptr(rot, cam4, light4, cfg.focal, hp)
+        t_e2e = (time.perf_counter() - t0) / args.steps
+        e2e_line = {"value": round(counts["rays"] / t_e2e / 1e6, 1), "unit": UNIT, "ms_per_step": round(t_e2e * 1e3, 4),
+                    "h2d_bytes_per_step": 84, "d2h_bytes_per_step": W * H * 4,
+                    "api": "rt_render (blocking: per-frame args + kernel + read-back into pinned host memory)"}
+    else:
+        # every rank: render tile -> all-gather -> rank 0 reads the whole frame back
+        def step_e2e():
+            r.render_device(rot, cam4, light4, cfg.focal, dev_ptr=frame.data_ptr(), stream=sptr)
+            dist.all_gather_into_tensor(frame, tile)
+            if rank == 0:
+                host.copy_(frame, non_blocking=True)
+            torch.cuda.synchronize()
+        for _ in range(3):
+            step_e2e()
+        dist.barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            step_e2e()
+        dist.barrier()
+        t_e2e = torch.tensor([(time.perf_counter() - t0) / args.steps], dtype=torch.float64, device=f"cuda:{local_rank}")
+        dist.all_reduce(t_e2e, op=dist.ReduceOp.MAX)
+        t_e2e = float(t_e2e.cpu())
+        e2e_line = {"value": round(counts["rays"] / t_e2e / 1e6, 1), "unit": UNIT, "ms_per_step": round(t_e2e * 1e3, 4),
+                    "h2d_bytes_per_step": 84, "d2h_bytes_per_step": W * H * 4,
+                    "api": "rt_render_device per rank + NCCL all-gather + read-back on rank 0"}
+
+    if rank == 0:
+        ms_per_step = total_step_ms / args.steps
+        kern_ms_per_step = total_kern_ms / args.steps
+        flops = algorithmic_flops(counts) / world  # per launch (one rank's tile; tiles are near-uniform)
+        achieved = flops / (kern_ms_per_step * 1e-3) / 1e12
+        nominal = 148 * 128 * 2 * 1.965e9 / 1e12
+        line = {
+            "metric": METRIC, "value": round(counts["rays"] / ms_per_step / 1e3, 1), "unit": UNIT, "n_gpus": world,
+            "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": round(ms_per_step, 4),
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": cfg.name, "description": cfg.description, "width": W, "height": H, "aa": cfg.aa,
+                       "shadow_samples": cfg.shadow_samples, "max_bounces": cfg.max_bounces, "focal": cfg.focal,
+                       "rays_per_frame": counts["rays"], "rays_source": "oracle counters (tests/golden/ray_counts.json)",
+                       "partition": f"{world} row tile(s) of {rows} rows" + (", in-place NCCL all-gather per frame" if world > 1 else ""),
+                       "l2": "flushed between timed iterations (256 MiB memset outside the timed event pairs); "
+                             "the scene is 3.4 KB and lives in shared memory",
+                       "arithmetic": "fast path (FMA, division-free shadow tests); RT_FLAG_STRICT_IEEE is the bit-exact anchor"},
+            "wall_ms_per_step_incl_flush": round(t_wall / args.steps * 1e3, 4),
+            "kernel_ms_per_step": round(kern_ms_per_step, 4),
+            "e2e": e2e_line,
+            "gpu_launches": int(launches),
+            "clocks": clocks,
+            "roofline": {"bound": "fp32", "kernel": "draw_brute_kernel<float,%d>" % (10 if cfg.shadow_samples % 10 == 0 else 8),
+                         "achieved": round(achieved, 3), "peak": round(fp32_peak, 3), "unit": "TFLOP/s",
+                         "frac": round(achieved / fp32_peak, 4) if fp32_peak else None,
+                         "peak_source": "FFMA microbenchmark in this run (rt_measure_fp32_peak); MEASURED_PEAKS.json has no FP32 entry",
+                         "peak_nominal": round(nominal, 1), "frac_of_nominal": round(achieved / nominal, 4),
+                         "algorithmic_gflop_per_launch": round(flops / 1e9, 3),
+                         "traffic": None},
+        }
+        # CPU baseline on this box's host cores (N = 1 only)
+        if world == 1 and not args.no_cpu_baseline:
+            step = pick_row_step(cfg)
+            best, rays, kind = None, 0, "reference"
+            t_budget = time.perf_counter()
+            for i in range(6):
+                t, rays, kind = cpu_reference_frame(cfg, step)
+                best = t if best is None else min(best, t)
+                if time.perf_counter() - t_budget > 15.0:
+                    break
+            line["cpu_baseline"] = {
+                "value": round(rays / best / 1e6, 2), "unit": UNIT, "cores": os.cpu_count(), "kind": kind,
+                "sample": f"{cfg.name}, " + ("all rows" if step == 1 else f"every {step}th row") +
+                          f", best of {i + 1} frames; verbatim kernels.cl via g++ shim (-O2, strict IEEE), all host threads",
+                "ms_per_frame": round(best * step * 1e3, 1)}
+        print(json.dumps(line), flush=True)
+    r.close()
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
+def main() -> int:
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
+    ap.add_argument("--workload", default="cfg2")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    import uob_raytracer_b200 as u
+    cfg = u.CONFIGS[args.workload]
+    if args.impl == "reference":
+        return run_reference(args, cfg)
+    return run_ours(args, cfg)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

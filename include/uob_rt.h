@@ -117,6 +117,11 @@ void rt_destroy(rt_ctx *ctx);
 /* Last error message of ctx (or of rt_create when ctx == NULL). Never NULL. */
 const char *rt_last_error(const rt_ctx *ctx);
 
+/* Diagnostic: measured FP32 FFMA throughput of this device in TFLOP/s (dependent-chain-free
+ * FFMA microbenchmark, best of 5, CUDA events) — the roofline denominator bench.py reports
+ * the render kernel against.  Not part of the reference's surface. */
+int rt_measure_fp32_peak(rt_ctx *ctx, float *tflops);
+
 /* Library version string, e.g. "uob_rt 0.1 (sm_100a)". */
 const char *rt_version(void);
 

@@ -47,6 +47,7 @@ RT_SYMBOLS = {
     "rt_scene_mode": (ctypes.c_char_p, [ctypes.c_void_p]),
     "rt_destroy": (None, [ctypes.c_void_p]),
     "rt_last_error": (ctypes.c_char_p, [ctypes.c_void_p]),
+    "rt_measure_fp32_peak": (ctypes.c_int, [ctypes.c_void_p, c_float_p]),
     "rt_version": (ctypes.c_char_p, []),
 }
 

@@ -114,6 +114,12 @@ class Renderer:
     def last_kernel_ms(self) -> float:
         return float(self._lib.rt_last_kernel_ms(self._ctx))
 
+    def measure_fp32_peak(self) -> float:
+        """FFMA microbenchmark on this device, TFLOP/s (roofline denominator)."""
+        out = ctypes.c_float(0)
+        self._check(self._lib.rt_measure_fp32_peak(self._ctx, ctypes.byref(out)))
+        return float(out.value)
+
     @property
     def kernel_launches(self) -> int:
         return int(self._lib.rt_kernel_launches(self._ctx))
