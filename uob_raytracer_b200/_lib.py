@@ -12,7 +12,7 @@ import ctypes
 import os
 
 PKG = os.path.dirname(os.path.abspath(__file__))
-RT_LIB_PATH = os.path.join(PKG, "libuob_rt.so")
+RT_LIB_PATH = os.environ.get("UOB_RT_LIB") or os.path.join(PKG, "libuob_rt.so")  # override: kernel-variant experiments only
 HOST_LIB_PATH = os.path.join(PKG, "libuob_host.so")
 
 c_float_p = ctypes.POINTER(ctypes.c_float)

@@ -11,7 +11,7 @@ import sys
 
 PKG = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(PKG, "csrc")
-LIB = os.path.join(PKG, "libuob_rt.so")
+LIB = os.environ.get("UOB_RT_LIB") or os.path.join(PKG, "libuob_rt.so")
 HOST_LIB = os.path.join(PKG, "libuob_host.so")
 HOST_SOURCES = [os.path.join("host", "uob_host.cpp")]
 HOST_FLAGS = ["-std=c++17", "-O2", "-ffp-contract=off", "-fno-fast-math", "-fPIC", "-shared", "-Wall"]
@@ -59,7 +59,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
     os.makedirs(os.path.join(PKG, "build"), exist_ok=True)
     for src in SOURCES:
         obj = os.path.join(PKG, "build", src.replace(".cu", ".o"))
-        cmd = [_nvcc(), *NVCC_FLAGS, "-c", os.path.join(CSRC, src), "-o", obj]
+        cmd = [_nvcc(), *NVCC_FLAGS, *os.environ.get("UOB_NVCC_DEFS", "").split(), "-c", os.path.join(CSRC, src), "-o", obj]
         if verbose:
             cmd.insert(1, "-Xptxas=-v")
             print(" ".join(cmd), file=sys.stderr)

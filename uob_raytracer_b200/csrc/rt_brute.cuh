@@ -43,6 +43,7 @@ struct SceneView {
   const float4 *ta, *tb, *tc;  // closest-hit triangles
   const float4 *tn, *tcol;     // normals, colours (w = material)
   const float4 *sa, *sb, *sc;  // shadow casters
+  const float4 *sd;            // shadow casters, fast path only: (kJitterMax*|N|, 0, 0, 0)
   int n, n_sh;
 };
 
@@ -51,6 +52,37 @@ template <class T> struct HitRec {
   V3<T> point, normal;
   float4 color;
 };
+
+// Sphere part of the closest-hit search (kernels.cl:132-163), continuing from current_t.
+template <class T>
+__device__ __forceinline__ void closest_spheres(V3<T> start, V3<T> dir, T current_t, HitRec<T> &hit) {
+#pragma unroll
+  for (int i = 0; i < RT_SPHERES; i++) {
+    const float4 cr = c_sphere_center_r2[i];
+    const V3<T> ctr = xyz<T>(cr);
+    const V3<T> L = start - ctr;
+    const T a = dot(dir, dir);
+    const T b = T(2.0f) * dot(dir, L);
+    const T c = dot(L, L) - T(cr.w);
+    const T disc = b * b - T(4.0f) * a * c;
+    if (disc < T(0.0f)) continue;
+    const T sq = sqrt_(disc);
+    const T q = (b > T(0.0f)) ? T(-0.5f) * (b + sq) : T(-0.5f) * (b - sq);
+    const T x0 = div_(q, a);
+    const T x1 = div_(c, q);
+    const T x_min = cl_min(x0, x1);
+    const T x_max = cl_max(x0, x1);
+    T x;
+    if (x_min >= T(0.0f) && x_min < current_t) x = x_min;
+    else if (x_max >= T(0.0f) && x_max < current_t) x = x_max;
+    else continue;
+    hit.id = -2;
+    hit.point = start + scale(x, dir);
+    hit.normal = normalize(hit.point - ctr);
+    hit.color = c_sphere_color[i];
+    current_t = x;
+  }
+}
 
 // ---------------------------------------------------------------------------
 // Closest hit: kernels.cl:92-166 / :168-241.
@@ -86,32 +118,7 @@ __device__ __forceinline__ void closest_hit(const SceneView &sc, V3<T> start, V3
     hit.normal = xyz<T>(sc.tn[best]);
     hit.color = sc.tcol[best];
   }
-#pragma unroll
-  for (int i = 0; i < RT_SPHERES; i++) {
-    const float4 cr = c_sphere_center_r2[i];
-    const V3<T> ctr = xyz<T>(cr);
-    const V3<T> L = start - ctr;
-    const T a = dot(dir, dir);
-    const T b = T(2.0f) * dot(dir, L);
-    const T c = dot(L, L) - T(cr.w);
-    const T disc = b * b - T(4.0f) * a * c;
-    if (disc < T(0.0f)) continue;
-    const T sq = sqrt_(disc);
-    const T q = (b > T(0.0f)) ? T(-0.5f) * (b + sq) : T(-0.5f) * (b - sq);
-    const T x0 = div_(q, a);
-    const T x1 = div_(c, q);
-    const T x_min = cl_min(x0, x1);
-    const T x_max = cl_max(x0, x1);
-    T x;
-    if (x_min >= T(0.0f) && x_min < current_t) x = x_min;
-    else if (x_max >= T(0.0f) && x_max < current_t) x = x_max;
-    else continue;
-    hit.id = -2;
-    hit.point = start + scale(x, dir);
-    hit.normal = normalize(hit.point - ctr);
-    hit.color = c_sphere_color[i];
-    current_t = x;
-  }
+  closest_spheres<T>(start, dir, current_t, hit);
 }
 
 // ---------------------------------------------------------------------------

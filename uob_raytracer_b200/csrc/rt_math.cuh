@@ -60,7 +60,7 @@ __device__ __forceinline__ float sqrt_approx(float x) {
 // work, where knife-edge decisions at the default camera are rounding
 // sensitive — SURVEY.md §7); the shadow path uses division-free tests.
 __device__ __forceinline__ float rcp_(float x) { return __frcp_rn(x); }
-__device__ __forceinline__ sfloat rcp_(sfloat x) { return sfloat(__fdiv_rn(1.0f, x.v)); }
+__device__ __forceinline__ sfloat rcp_(sfloat x) { return sfloat(__frcp_rn(x.v)); }  // rcp.rn: correctly rounded == 1.0f/x
 __device__ __forceinline__ float div_(float a, float b) { return __fdiv_rn(a, b); }
 __device__ __forceinline__ sfloat div_(sfloat a, sfloat b) { return sfloat(__fdiv_rn(a.v, b.v)); }
 __device__ __forceinline__ float sqrt_(float x) { return __fsqrt_rn(x); }
