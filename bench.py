@@ -309,7 +309,7 @@ def run_ours(args, cfg) -> int:
             "e2e": e2e_line,
             "gpu_launches": int(launches),
             "clocks": clocks,
-            "roofline": {"bound": "fp32", "kernel": "draw_brute_kernel<float,%d>" % (10 if cfg.shadow_samples % 10 == 0 else 8),
+            "roofline": {"bound": "fp32", "kernel": "draw_fast_kernel<%d,%d,true>" % (10 if cfg.shadow_samples % 10 == 0 else 8, 4 if (cfg.aa * cfg.aa) % 4 == 0 else 1),
                          "achieved": round(achieved, 3), "peak": round(fp32_peak, 3), "unit": "TFLOP/s",
                          "frac": round(achieved / fp32_peak, 4) if fp32_peak else None,
                          "peak_source": "FFMA microbenchmark in this run (rt_measure_fp32_peak); MEASURED_PEAKS.json has no FP32 entry",

@@ -51,20 +51,35 @@ def build_host(force: bool = False) -> str:
     return HOST_LIB
 
 
+FAST_CHUNKS = [1, 2, 4, 5, 8, 10]
+
+
 def build(force: bool = False, verbose: bool = False) -> str:
     build_host(force)
     if not force and not needs_build():
         return LIB
-    objs = []
+    from concurrent.futures import ThreadPoolExecutor
     os.makedirs(os.path.join(PKG, "build"), exist_ok=True)
-    for src in SOURCES:
-        obj = os.path.join(PKG, "build", src.replace(".cu", ".o"))
-        cmd = [_nvcc(), *NVCC_FLAGS, *os.environ.get("UOB_NVCC_DEFS", "").split(), "-c", os.path.join(CSRC, src), "-o", obj]
+    extra = os.environ.get("UOB_NVCC_DEFS", "").split()
+    jobs = [(src, [], src.replace(".cu", ".o")) for src in SOURCES]
+    jobs += [("rt_draw_fast.cu", [f"-DRT_FAST_CH={ch}"], f"rt_draw_fast_ch{ch}.o") for ch in FAST_CHUNKS]
+
+    def compile_one(job):
+        src, defs, obj = job
+        obj = os.path.join(PKG, "build", obj)
+        cmd = [_nvcc(), *NVCC_FLAGS, *extra, *defs, "-c", os.path.join(CSRC, src), "-o", obj]
         if verbose:
             cmd.insert(1, "-Xptxas=-v")
-            print(" ".join(cmd), file=sys.stderr)
-        subprocess.check_call(cmd)
-        objs.append(obj)
+        out = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+        if out.returncode != 0:
+            raise RuntimeError(f"nvcc failed for {src} {defs}:\n{out.stdout}")
+        return out.stdout
+
+    with ThreadPoolExecutor(max_workers=min(8, os.cpu_count() or 1)) as ex:
+        logs = list(ex.map(compile_one, jobs))
+    if verbose:
+        sys.stderr.write("".join(logs))
+    objs = [os.path.join(PKG, "build", j[2]) for j in jobs]
     cmd = [_nvcc(), "-Wno-deprecated-gpu-targets", "-shared", "-o", LIB, *objs, "-lcudart"]
     subprocess.check_call(cmd)
     return LIB

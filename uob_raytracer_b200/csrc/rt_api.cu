@@ -134,9 +134,9 @@ int rt_upload_scene(rt_ctx *ctx, const float *verts, const float *normals, const
   // Per-triangle constants, computed with the single-rounded operations the
   // reference kernel performs per ray (kernels.cl:102-104 and the cofactors of
   // det, :31-35).  volatile keeps the host compiler from contracting a*b-c*d.
-  std::vector<float4> h(5 * (size_t)n + 4 * (size_t)n_sh);
+  std::vector<float4> h(5 * (size_t)n + 7 * (size_t)n_sh);
   float4 *ta = h.data(), *tb = ta + n, *tc = tb + n, *tn = tc + n, *tcol = tn + n;
-  float4 *sa = tcol + n, *sb = sa + n_sh, *sc = sb + n_sh, *sd = sc + n_sh;
+  float4 *sa = tcol + n, *sb = sa + n_sh, *sc = sb + n_sh, *rec = sc + n_sh;
   int k = 0;
   for (int i = 0; i < n; i++) {
     const float *v0 = verts + 12 * (size_t)i, *v1 = v0 + 4, *v2 = v0 + 8;
@@ -153,8 +153,13 @@ int rt_upload_scene(rt_ctx *ctx, const float *verts, const float *normals, const
       sa[k] = ta[i];
       sb[k] = tb[i];
       sc[k] = tc[i];
-      // fast path: bound on |j.N| over all jitters j of the area light (rt_fast.cuh); 0.0445 = kJitterMax
-      sd[k] = make_float4(0.0445f * sqrtf(c0 * c0 + c1 * c1 + c2 * c2), 0.0f, 0.0f, 0.0f);
+      // fast-path record (rt_fast.cuh): bounds on |j.N|, |j|*|e1|, |j|*|e2| over all jitters j of the
+      // area light; 0.0445 = kJitterMax
+      const float kj = 0.0445f;
+      rec[4 * k + 0] = make_float4(v0[0], v0[1], v0[2], kj * sqrtf(c0 * c0 + c1 * c1 + c2 * c2));
+      rec[4 * k + 1] = make_float4(c0, c1, c2, 0.0f);
+      rec[4 * k + 2] = make_float4(e1x, e1y, e1z, kj * sqrtf(e1x * e1x + e1y * e1y + e1z * e1z));
+      rec[4 * k + 3] = make_float4(e2x, e2y, e2z, kj * sqrtf(e2x * e2x + e2y * e2y + e2z * e2z));
       k++;
     }
   }

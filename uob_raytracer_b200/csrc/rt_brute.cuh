@@ -22,8 +22,8 @@ namespace rt {
 // Analytic spheres baked into the reference kernel (kernels.cl:7-10): centre.xyz,
 // radius^2 in .w; colour.w is the material (-1 glass, 0 mirror).
 #define RT_SPHERES 2
-__constant__ float4 c_sphere_center_r2[RT_SPHERES] = {{0.3f, 0.1f, -0.5f, 0.075f}, {-0.4f, 0.8f, -0.5f, 0.05f}};
-__constant__ float4 c_sphere_color[RT_SPHERES] = {{0.0f, 0.0f, 0.0f, -1.0f}, {0.0f, 0.0f, 0.0f, 0.0f}};
+static __constant__ float4 c_sphere_center_r2[RT_SPHERES] = {{0.3f, 0.1f, -0.5f, 0.075f}, {-0.4f, 0.8f, -0.5f, 0.05f}};
+static __constant__ float4 c_sphere_color[RT_SPHERES] = {{0.0f, 0.0f, 0.0f, -1.0f}, {0.0f, 0.0f, 0.0f, 0.0f}};
 
 #define RT_GLASS 1.52f
 #define RT_AIR 1.0f
@@ -43,7 +43,6 @@ struct SceneView {
   const float4 *ta, *tb, *tc;  // closest-hit triangles
   const float4 *tn, *tcol;     // normals, colours (w = material)
   const float4 *sa, *sb, *sc;  // shadow casters
-  const float4 *sd;            // shadow casters, fast path only: (kJitterMax*|N|, 0, 0, 0)
   int n, n_sh;
 };
 

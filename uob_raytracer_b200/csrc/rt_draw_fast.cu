@@ -1,0 +1,190 @@
+// rt_draw_fast.cu — the fast `draw` kernel (see rt_fast.cuh for the method).  Compiled once per
+// shadow chunk size: -DRT_FAST_CH=n gives launch_fast_ch<n>.
+#include "rt_launch.cuh"
+
+#ifndef RT_FAST_CH
+#define RT_FAST_CH 8
+#endif
+
+namespace rt {
+
+// CH shadow samples per chunk, RB primary rays of a pixel per triangle load, SINGLE = (S == CH).
+template <int CH, int RB, bool SINGLE>
+__global__ void __launch_bounds__(kThreads, RT_MINBLOCKS) draw_fast_kernel(const __grid_constant__ FrameParams p,
+                                                                           const float4 *__restrict__ scene, int n, int n_sh) {
+  extern __shared__ float4 smem[];
+  __shared__ int s_warp_count[kThreads / 32];
+  __shared__ int s_base;
+
+  // ---- stage the scene: generic arrays [0,5n) and the shadow records (global offset 5n+3n_sh) ----
+  float4 *const gen = smem;
+  float4 *const prim = smem + 5 * n;
+  float4 *const shad = prim + 3 * n;
+  int *const plist = reinterpret_cast<int *>(shad + 4 * n_sh);
+  for (int i = threadIdx.x; i < 5 * n; i += kThreads) gen[i] = scene[i];
+  for (int i = threadIdx.x; i < 4 * n_sh; i += kThreads) shad[i] = scene[5 * n + 3 * n_sh + i];
+  if (threadIdx.x == 0) s_base = 0;
+  FastScene sc;
+  sc.g.ta = gen;
+  sc.g.tb = gen + n;
+  sc.g.tc = gen + 2 * n;
+  sc.g.tn = gen + 3 * n;
+  sc.g.tcol = gen + 4 * n;
+  sc.g.sa = sc.g.sb = sc.g.sc = nullptr;  // the SoA shadow arrays belong to the generic kernel
+  sc.g.n = n;
+  sc.g.n_sh = n_sh;
+  sc.prim = prim;
+  sc.shad = shad;
+  sc.plist = plist;
+  const V3<float> cam(p.cam[0], p.cam[1], p.cam[2]), light(p.light[0], p.light[1], p.light[2]);
+  const int A = p.A, S = p.S;
+  const float SW = (float)p.W, SH = (float)p.H, fA = (float)A;
+  __syncthreads();
+
+  // ---- per-triangle camera constants + binning of the triangles against this block's tile ----
+  {
+    // corner rays of the tile in virtual (sub-pixel) coordinates, un-normalised (kernels.cl:384-400)
+    const float vx0 = (float)(blockIdx.x * kTileW * A) - SW * fA * 0.5f;
+    const float vy0 = (float)((p.row0 + blockIdx.y * kTileH) * A) - SH * fA * 0.5f;
+    const float vx1 = vx0 + (float)(kTileW * A - 1), vy1 = vy0 + (float)(kTileH * A - 1);
+    V3<float> dc[4];
+    float dmax = 0.0f;
+#pragma unroll
+    for (int c = 0; c < 4; c++) {
+      const float vx = (c & 1) ? vx1 : vx0, vy = (c & 2) ? vy1 : vy0;
+      dc[c] = V3<float>(p.rot[0] * vx + p.rot[1] * vy + p.rot[2] * p.focal, p.rot[3] * vx + p.rot[4] * vy + p.rot[5] * p.focal,
+                        p.rot[6] * vx + p.rot[7] * vy + p.rot[8] * p.focal);
+      dmax = fmaxf(dmax, sqrtf(dot(dc[c], dc[c])));
+    }
+    dmax *= 1.001f;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int base = 0; base < n; base += kThreads) {
+      const int i = base + threadIdx.x;
+      bool keep = false;
+      if (i < n) {
+        primary_constants(sc.g, prim, cam, i);
+        keep = tile_may_hit(prim, i, dc, dmax);
+      }
+      const unsigned ballot = __ballot_sync(0xffffffffu, keep);
+      if (lane == 0) s_warp_count[warp] = __popc(ballot);
+      __syncthreads();
+      int offset = s_base, total = 0;
+#pragma unroll
+      for (int w = 0; w < kThreads / 32; w++) {
+        const int c = s_warp_count[w];
+        offset += (w < warp) ? c : 0;
+        total += c;
+      }
+      if (keep) plist[offset + __popc(ballot & ((1u << lane) - 1u))] = i;
+      __syncthreads();
+      if (threadIdx.x == 0) s_base += total;
+    }
+    __syncthreads();
+    sc.n_prim = s_base;
+  }
+
+  int x, y;
+  if (!pixel_of_thread(p, x, y)) return;
+
+  const int global_id = __float2int_rz(__fadd_rn(__fmul_rn((float)y, SW), (float)x));  // kernels.cl:380, float arithmetic
+  Jitters<CH> jit;
+  if constexpr (SINGLE) {
+    uint32_t rx, ry, rz;
+    seed_rng(global_id, rx, ry, rz);
+    make_jitters<CH>(rx, ry, rz, jit);
+  }
+  // Primary ray directions with the reference's operation sequence (kernels.cl:384-405): a handful
+  // of operations per ray, and it makes the primary hits bit-identical to the reference.
+  typedef sfloat SF;
+  const V3<SF> base(SF((float)(x * A)) - div_(SF(SW) * SF(fA), SF(2.0f)), SF((float)(y * A)) - div_(SF(SH) * SF(fA), SF(2.0f)), SF(p.focal));
+  const V3<SF> r0(SF(p.rot[0]), SF(p.rot[1]), SF(p.rot[2])), r1(SF(p.rot[3]), SF(p.rot[4]), SF(p.rot[5])),
+      r2(SF(p.rot[6]), SF(p.rot[7]), SF(p.rot[8]));
+  const V3<SF> cam_s(SF(cam.x), SF(cam.y), SF(cam.z));
+  V3<float> total(0.0f, 0.0f, 0.0f);
+  const int rays = A * A;
+#pragma unroll 1
+  for (int r0i = 0; r0i < rays; r0i += RB) {
+    float dirx[RB], diry[RB], dirz[RB];
+#pragma unroll
+    for (int k = 0; k < RB; k++) {
+      const int idx = r0i + k;  // ray index dy*A + dx (kernels.cl:393-397)
+      const int dy = idx / A, dx = idx - dy * A;
+      const V3<SF> d0 = base + V3<SF>(SF((float)dx), SF((float)dy), SF(0.0f));
+      const V3<SF> dn = normalize(V3<SF>(dot(r0, d0), dot(r1, d0), dot(r2, d0)));
+      dirx[k] = dn.x.v;
+      diry[k] = dn.y.v;
+      dirz[k] = dn.z.v;
+    }
+    int best[RB];
+    float bt[RB], bu[RB], bv[RB];
+    primary_triangles<RB>(sc, dirx, diry, dirz, best, bt, bu, bv);
+
+    // One copy of the shading code: the rays of the batch are selected by index.
+#pragma unroll 1
+    for (int k = 0; k < RB; k++) {
+      V3<float> dir(sel(dirx, k), sel(diry, k), sel(dirz, k));
+      const int bi = sel(best, k);
+      HitRec<float> hit;
+      {
+        HitRec<SF> hs;
+        hs.id = -1;
+        hs.color = make_float4(0.0f, 0.0f, 0.0f, 1.0f);
+        hs.point = V3<SF>(SF(0.0f), SF(0.0f), SF(0.0f));
+        hs.normal = hs.point;
+        if (bi >= 0) {
+          const V3<SF> v0 = xyz<SF>(sc.g.ta[bi]), e1 = xyz<SF>(sc.g.tb[bi]), e2 = xyz<SF>(sc.g.tc[bi]);
+          hs.id = bi;
+          hs.point = (v0 + scale(SF(sel(bu, k)), e1)) + scale(SF(sel(bv, k)), e2);  // kernels.cl:124
+          hs.normal = xyz<SF>(sc.g.tn[bi]);
+          hs.color = sc.g.tcol[bi];
+        }
+        // the two spheres, strict as well
+        closest_spheres<SF>(cam_s, V3<SF>(SF(dir.x), SF(dir.y), SF(dir.z)), SF(sel(bt, k)), hs);
+        hit.id = hs.id;
+        hit.point = V3<float>(hs.point.x.v, hs.point.y.v, hs.point.z.v);
+        hit.normal = V3<float>(hs.normal.x.v, hs.normal.y.v, hs.normal.z.v);
+        hit.color = hs.color;
+      }
+      // direct light of a diffuse hit, or secondary_light's bounce loop (kernels.cl:342-365) ending in
+      // the same shading — a single call site for both
+      float medium = RT_AIR, gain = 1.0f;
+      int bounce = 0;
+      while (hit.id != -1) {
+        if (hit.color.w > 0.0f) {
+          const float fl = gain * (RT_INDIRECT + direct_light_fast<CH, SINGLE>(sc, hit.point, hit.normal, light, S, global_id, jit));
+          total = V3<float>(total.x + hit.color.x * fl, total.y + hit.color.y * fl, total.z + hit.color.z * fl);
+          break;
+        }
+        if (bounce >= p.B) break;
+        bounce++;
+        V3<float> start, ndir;
+        if (hit.color.w == 0.0f) reflect_ray<float>(dir, hit.normal, hit.point, start, ndir, medium);
+        else refract_ray<float>(dir, hit.normal, hit.point, medium, start, ndir, medium);
+        dir = ndir;
+        hit.id = -1;
+        hit.color.w = 1.0f;
+        closest_hit<float>(sc.g, start, dir, hit);
+        gain = 0.9f;
+      }
+    }
+  }
+  const float ia = 1.0f / (float)rays;
+  p.out[(size_t)y * p.W + x] = pack_argb<float>(V3<float>(total.x * ia, total.y * ia, total.z * ia));
+}
+
+#define RT_CAT2(a, b) a##b
+#define RT_CAT(a, b) RT_CAT2(a, b)
+
+// Primary rays: 4 per triangle load when aa*aa % 4 == 0.
+cudaError_t RT_CAT(launch_fast_ch, RT_FAST_CH)(rt_ctx *ctx, const FrameParams &fp, cudaStream_t stream) {
+  constexpr int CH = RT_FAST_CH;
+  const bool rb4 = (fp.A * fp.A) % 4 == 0;
+  if (fp.S == CH) {
+    if (rb4) return launch_kernel(draw_fast_kernel<CH, 4, true>, ctx, fp, stream);
+    return launch_kernel(draw_fast_kernel<CH, 1, true>, ctx, fp, stream);
+  }
+  if (rb4) return launch_kernel(draw_fast_kernel<CH, 4, false>, ctx, fp, stream);
+  return launch_kernel(draw_fast_kernel<CH, 1, false>, ctx, fp, stream);
+}
+
+}  // namespace rt

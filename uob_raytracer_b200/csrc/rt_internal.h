@@ -19,7 +19,8 @@ struct rt_ctx {
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   bool timed = false;
   uint32_t *d_frame = nullptr;  // whole frame, W*H
-  // Brute-force scene: one float4 buffer, [ta|tb|tc|tn|tcol] x n then [sa|sb|sc] x n_sh
+  // Brute-force scene: one float4 buffer, [ta|tb|tc|tn|tcol] x n, [sa|sb|sc] x n_sh (generic kernel),
+  // then 4 float4 per shadow caster (fast kernel, rt_fast.cuh)
   float4 *d_scene = nullptr;
   int n = 0, n_sh = 0;
   bool have_scene = false;
@@ -35,5 +36,12 @@ namespace rt {
 cudaError_t launch_draw_brute(rt_ctx *ctx, const FrameParams &fp, cudaStream_t stream);
 size_t brute_smem_bytes(int n, int n_sh);
 size_t brute_smem_limit();
+// rt_draw_fast.cu, one translation unit per shadow chunk size
+cudaError_t launch_fast_ch1(rt_ctx *ctx, const FrameParams &fp, cudaStream_t stream);
+cudaError_t launch_fast_ch2(rt_ctx *ctx, const FrameParams &fp, cudaStream_t stream);
+cudaError_t launch_fast_ch4(rt_ctx *ctx, const FrameParams &fp, cudaStream_t stream);
+cudaError_t launch_fast_ch5(rt_ctx *ctx, const FrameParams &fp, cudaStream_t stream);
+cudaError_t launch_fast_ch8(rt_ctx *ctx, const FrameParams &fp, cudaStream_t stream);
+cudaError_t launch_fast_ch10(rt_ctx *ctx, const FrameParams &fp, cudaStream_t stream);
 
 }  // namespace rt
