@@ -15,6 +15,7 @@ __global__ void __launch_bounds__(kThreads, RT_MINBLOCKS) draw_fast_kernel(const
   extern __shared__ float4 smem[];
   __shared__ int s_warp_count[kThreads / 32];
   __shared__ int s_base;
+  __shared__ int s_spheres_visible;
 
   // ---- stage the scene: generic arrays [0,5n) and the shadow records (global offset 5n+3n_sh) ----
   float4 *const gen = smem;
@@ -57,6 +58,33 @@ __global__ void __launch_bounds__(kThreads, RT_MINBLOCKS) draw_fast_kernel(const
       dmax = fmaxf(dmax, sqrtf(dot(dc[c], dc[c])));
     }
     dmax *= 1.001f;
+    if (threadIdx.x == 0) {
+      // Can any primary ray of the tile hit a sphere?  The tile's rays lie in a cone of half-angle th_t
+      // around the centre ray; a sphere is seen from the camera inside a cone of half-angle th_s around
+      // the direction to its centre.  No hit if the axes are further apart than th_t + th_s.
+      const V3<float> dm((dc[0].x + dc[3].x) * 0.5f, (dc[0].y + dc[3].y) * 0.5f, (dc[0].z + dc[3].z) * 0.5f);
+      const float im = rsqrtf(dot(dm, dm));
+      float cos_t = 1.0f;
+#pragma unroll
+      for (int c = 0; c < 4; c++) cos_t = fminf(cos_t, dot(dm, dc[c]) * im * rsqrtf(dot(dc[c], dc[c])));
+      cos_t = fminf(cos_t - 1e-5f, 1.0f);
+      const float sin_t = sqrtf(fmaxf(1.0f - cos_t * cos_t, 0.0f));
+      int vis = 0;
+#pragma unroll
+      for (int i = 0; i < RT_SPHERES; i++) {
+        const float4 cr = c_sphere_center_r2[i];
+        const V3<float> L(cr.x - cam.x, cr.y - cam.y, cr.z - cam.z);
+        const float l2 = dot(L, L);
+        bool may = true;
+        if (l2 > cr.w * 1.0001f) {
+          const float sin_s = fminf(sqrtf(cr.w / l2) * 1.0001f, 1.0f), cos_s = sqrtf(fmaxf(1.0f - sin_s * sin_s, 0.0f));
+          const float cos_sum = (cos_t > 0.0f) ? cos_t * cos_s - sin_t * sin_s : -1.0f;  // th_t + th_s (no cull for huge tiles)
+          may = dot(dm, L) * im * rsqrtf(l2) >= cos_sum - 1e-4f;
+        }
+        vis |= may ? 1 : 0;
+      }
+      s_spheres_visible = vis;
+    }
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     for (int base = 0; base < n; base += kThreads) {
       const int i = base + threadIdx.x;
@@ -82,17 +110,14 @@ __global__ void __launch_bounds__(kThreads, RT_MINBLOCKS) draw_fast_kernel(const
     __syncthreads();
     sc.n_prim = s_base;
   }
+  const bool spheres_visible = s_spheres_visible != 0;
 
   int x, y;
   if (!pixel_of_thread(p, x, y)) return;
 
   const int global_id = __float2int_rz(__fadd_rn(__fmul_rn((float)y, SW), (float)x));  // kernels.cl:380, float arithmetic
-  Jitters<CH> jit;
-  if constexpr (SINGLE) {
-    uint32_t rx, ry, rz;
-    seed_rng(global_id, rx, ry, rz);
-    make_jitters<CH>(rx, ry, rz, jit);
-  }
+  Jitters<CH> jit;        // SINGLE: the pixel's S jitters, generated on the first shading point
+  bool have_jit = false;  // (44 % of the 1080p frame lies outside the box and never shades)
   // Primary ray directions with the reference's operation sequence (kernels.cl:384-405): a handful
   // of operations per ray, and it makes the primary hits bit-identical to the reference.
   typedef sfloat SF;
@@ -102,13 +127,17 @@ __global__ void __launch_bounds__(kThreads, RT_MINBLOCKS) draw_fast_kernel(const
   const V3<SF> cam_s(SF(cam.x), SF(cam.y), SF(cam.z));
   V3<float> total(0.0f, 0.0f, 0.0f);
   const int rays = A * A;
+  int ray_dx = 0, ray_dy = 0;  // ray index dy*A + dx (kernels.cl:393-397), advanced without dividing
 #pragma unroll 1
   for (int r0i = 0; r0i < rays; r0i += RB) {
     float dirx[RB], diry[RB], dirz[RB];
 #pragma unroll
     for (int k = 0; k < RB; k++) {
-      const int idx = r0i + k;  // ray index dy*A + dx (kernels.cl:393-397)
-      const int dy = idx / A, dx = idx - dy * A;
+      const int dx = ray_dx, dy = ray_dy;
+      if (++ray_dx == A) {
+        ray_dx = 0;
+        ray_dy++;
+      }
       const V3<SF> d0 = base + V3<SF>(SF((float)dx), SF((float)dy), SF(0.0f));
       const V3<SF> dn = normalize(V3<SF>(dot(r0, d0), dot(r1, d0), dot(r2, d0)));
       dirx[k] = dn.x.v;
@@ -138,8 +167,8 @@ __global__ void __launch_bounds__(kThreads, RT_MINBLOCKS) draw_fast_kernel(const
           hs.normal = xyz<SF>(sc.g.tn[bi]);
           hs.color = sc.g.tcol[bi];
         }
-        // the two spheres, strict as well
-        closest_spheres<SF>(cam_s, V3<SF>(SF(dir.x), SF(dir.y), SF(dir.z)), SF(sel(bt, k)), hs);
+        // the two spheres, strict as well (skipped when no ray of the block's tile can reach one)
+        if (spheres_visible) closest_spheres<SF>(cam_s, V3<SF>(SF(dir.x), SF(dir.y), SF(dir.z)), SF(sel(bt, k)), hs);
         hit.id = hs.id;
         hit.point = V3<float>(hs.point.x.v, hs.point.y.v, hs.point.z.v);
         hit.normal = V3<float>(hs.normal.x.v, hs.normal.y.v, hs.normal.z.v);
@@ -151,6 +180,12 @@ __global__ void __launch_bounds__(kThreads, RT_MINBLOCKS) draw_fast_kernel(const
       int bounce = 0;
       while (hit.id != -1) {
         if (hit.color.w > 0.0f) {
+          if (SINGLE && !have_jit) {
+            uint32_t rx, ry, rz;
+            seed_rng(global_id, rx, ry, rz);
+            make_jitters<CH>(rx, ry, rz, jit);
+            have_jit = true;
+          }
           const float fl = gain * (RT_INDIRECT + direct_light_fast<CH, SINGLE>(sc, hit.point, hit.normal, light, S, global_id, jit));
           total = V3<float>(total.x + hit.color.x * fl, total.y + hit.color.y * fl, total.z + hit.color.z * fl);
           break;
