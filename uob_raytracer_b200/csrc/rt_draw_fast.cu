@@ -8,8 +8,8 @@
 
 namespace rt {
 
-// CH shadow samples per chunk, RB primary rays of a pixel per triangle load, SINGLE = (S == CH).
-template <int CH, int RB, bool SINGLE>
+// CH shadow samples per chunk, SINGLE = (S == CH).
+template <int CH, bool SINGLE>
 __global__ void __launch_bounds__(kThreads, RT_MINBLOCKS) draw_fast_kernel(const __grid_constant__ FrameParams p,
                                                                            const float4 *__restrict__ scene, int n, int n_sh) {
   extern __shared__ float4 smem[];
@@ -22,6 +22,8 @@ __global__ void __launch_bounds__(kThreads, RT_MINBLOCKS) draw_fast_kernel(const
   float4 *const prim = smem + 5 * n;
   float4 *const shad = prim + 3 * n;
   int *const plist = reinterpret_cast<int *>(shad + 4 * n_sh);
+  // per-thread jitter columns (SINGLE only), after the triangle list
+  float *const jit_base = reinterpret_cast<float *>(smem + scene_smem_float4(n, n_sh));
   for (int i = threadIdx.x; i < 5 * n; i += kThreads) gen[i] = scene[i];
   for (int i = threadIdx.x; i < 4 * n_sh; i += kThreads) shad[i] = scene[5 * n + 3 * n_sh + i];
   if (threadIdx.x == 0) s_base = 0;
@@ -116,8 +118,11 @@ __global__ void __launch_bounds__(kThreads, RT_MINBLOCKS) draw_fast_kernel(const
   if (!pixel_of_thread(p, x, y)) return;
 
   const int global_id = __float2int_rz(__fadd_rn(__fmul_rn((float)y, SW), (float)x));  // kernels.cl:380, float arithmetic
-  Jitters<CH> jit;        // SINGLE: the pixel's S jitters, generated on the first shading point
-  bool have_jit = false;  // (44 % of the 1080p frame lies outside the box and never shades)
+  // SINGLE: the pixel's S jitters, generated on the first shading point (44 % of the 1080p frame
+  // lies outside the box and never shades) and kept in shared memory
+  JittersShared<CH, kThreads> jit;
+  jit.p = jit_base + threadIdx.x;
+  bool have_jit = false;
   // Primary ray directions with the reference's operation sequence (kernels.cl:384-405): a handful
   // of operations per ray, and it makes the primary hits bit-identical to the reference.
   typedef sfloat SF;
@@ -127,32 +132,18 @@ __global__ void __launch_bounds__(kThreads, RT_MINBLOCKS) draw_fast_kernel(const
   const V3<SF> cam_s(SF(cam.x), SF(cam.y), SF(cam.z));
   V3<float> total(0.0f, 0.0f, 0.0f);
   const int rays = A * A;
-  int ray_dx = 0, ray_dy = 0;  // ray index dy*A + dx (kernels.cl:393-397), advanced without dividing
+  // One primary ray at a time, in the reference's order dy*A + dx (kernels.cl:393-397); the
+  // block's binned triangle list is short, so nothing is gained by batching rays.
 #pragma unroll 1
-  for (int r0i = 0; r0i < rays; r0i += RB) {
-    float dirx[RB], diry[RB], dirz[RB];
-#pragma unroll
-    for (int k = 0; k < RB; k++) {
-      const int dx = ray_dx, dy = ray_dy;
-      if (++ray_dx == A) {
-        ray_dx = 0;
-        ray_dy++;
-      }
-      const V3<SF> d0 = base + V3<SF>(SF((float)dx), SF((float)dy), SF(0.0f));
-      const V3<SF> dn = normalize(V3<SF>(dot(r0, d0), dot(r1, d0), dot(r2, d0)));
-      dirx[k] = dn.x.v;
-      diry[k] = dn.y.v;
-      dirz[k] = dn.z.v;
-    }
-    int best[RB];
-    float bt[RB], bu[RB], bv[RB];
-    primary_triangles<RB>(sc, dirx, diry, dirz, best, bt, bu, bv);
-
-    // One copy of the shading code: the rays of the batch are selected by index.
+  for (int ray_dy = 0; ray_dy < A; ray_dy++) {
 #pragma unroll 1
-    for (int k = 0; k < RB; k++) {
-      V3<float> dir(sel(dirx, k), sel(diry, k), sel(dirz, k));
-      const int bi = sel(best, k);
+    for (int ray_dx = 0; ray_dx < A; ray_dx++) {
+      const V3<SF> d0 = base + V3<SF>(SF((float)ray_dx), SF((float)ray_dy), SF(0.0f));
+      const V3<SF> dns = normalize(V3<SF>(dot(r0, d0), dot(r1, d0), dot(r2, d0)));
+      V3<float> dir(dns.x.v, dns.y.v, dns.z.v);
+      int bi;
+      float bt, bu, bv;
+      primary_triangles(sc, dir, bi, bt, bu, bv);
       HitRec<float> hit;
       {
         HitRec<SF> hs;
@@ -163,12 +154,12 @@ __global__ void __launch_bounds__(kThreads, RT_MINBLOCKS) draw_fast_kernel(const
         if (bi >= 0) {
           const V3<SF> v0 = xyz<SF>(sc.g.ta[bi]), e1 = xyz<SF>(sc.g.tb[bi]), e2 = xyz<SF>(sc.g.tc[bi]);
           hs.id = bi;
-          hs.point = (v0 + scale(SF(sel(bu, k)), e1)) + scale(SF(sel(bv, k)), e2);  // kernels.cl:124
+          hs.point = (v0 + scale(SF(bu), e1)) + scale(SF(bv), e2);  // kernels.cl:124
           hs.normal = xyz<SF>(sc.g.tn[bi]);
           hs.color = sc.g.tcol[bi];
         }
         // the two spheres, strict as well (skipped when no ray of the block's tile can reach one)
-        if (spheres_visible) closest_spheres<SF>(cam_s, V3<SF>(SF(dir.x), SF(dir.y), SF(dir.z)), SF(sel(bt, k)), hs);
+        if (spheres_visible) closest_spheres<SF>(cam_s, dns, SF(bt), hs);
         hit.id = hs.id;
         hit.point = V3<float>(hs.point.x.v, hs.point.y.v, hs.point.z.v);
         hit.normal = V3<float>(hs.normal.x.v, hs.normal.y.v, hs.normal.z.v);
@@ -183,10 +174,12 @@ __global__ void __launch_bounds__(kThreads, RT_MINBLOCKS) draw_fast_kernel(const
           if (SINGLE && !have_jit) {
             uint32_t rx, ry, rz;
             seed_rng(global_id, rx, ry, rz);
-            make_jitters<CH>(rx, ry, rz, jit);
+            Jitters<CH> jr;
+            make_jitters<CH>(rx, ry, rz, jr);
+            jit.store(jr);
             have_jit = true;
           }
-          const float fl = gain * (RT_INDIRECT + direct_light_fast<CH, SINGLE>(sc, hit.point, hit.normal, light, S, global_id, jit));
+          const float fl = gain * (RT_INDIRECT + direct_light_fast<CH, SINGLE, JittersShared<CH, kThreads>>(sc, hit.point, hit.normal, light, S, global_id, jit));
           total = V3<float>(total.x + hit.color.x * fl, total.y + hit.color.y * fl, total.z + hit.color.z * fl);
           break;
         }
@@ -203,23 +196,18 @@ __global__ void __launch_bounds__(kThreads, RT_MINBLOCKS) draw_fast_kernel(const
       }
     }
   }
-  const float ia = 1.0f / (float)rays;
+  const float ia = 1.0f / (float)(A * A);
   p.out[(size_t)y * p.W + x] = pack_argb<float>(V3<float>(total.x * ia, total.y * ia, total.z * ia));
 }
 
 #define RT_CAT2(a, b) a##b
 #define RT_CAT(a, b) RT_CAT2(a, b)
 
-// Primary rays: 4 per triangle load when aa*aa % 4 == 0.
 cudaError_t RT_CAT(launch_fast_ch, RT_FAST_CH)(rt_ctx *ctx, const FrameParams &fp, cudaStream_t stream) {
   constexpr int CH = RT_FAST_CH;
-  const bool rb4 = (fp.A * fp.A) % 4 == 0;
-  if (fp.S == CH) {
-    if (rb4) return launch_kernel(draw_fast_kernel<CH, 4, true>, ctx, fp, stream);
-    return launch_kernel(draw_fast_kernel<CH, 1, true>, ctx, fp, stream);
-  }
-  if (rb4) return launch_kernel(draw_fast_kernel<CH, 4, false>, ctx, fp, stream);
-  return launch_kernel(draw_fast_kernel<CH, 1, false>, ctx, fp, stream);
+  ctx->launch_extra_smem = sizeof(float) * 3 * CH * kThreads;  // jitter columns
+  if (fp.S == CH) return launch_kernel(draw_fast_kernel<CH, true>, ctx, fp, stream);
+  return launch_kernel(draw_fast_kernel<CH, false>, ctx, fp, stream);
 }
 
 }  // namespace rt

@@ -109,53 +109,64 @@ __device__ __forceinline__ bool tile_may_hit(const float4 *prim, int i, const V3
   return !(out1 | out2 | out3);
 }
 
-// Closest triangle for RB rays from the camera (kernels.cl:100-129); see the header.
+// Closest triangle for one ray from the camera (kernels.cl:100-129); see the header.
 // best = -1 on a miss; bt = t, bu/bv = barycentrics (all strict values).
-template <int RB>
-__device__ __forceinline__ void primary_triangles(const FastScene &sc, const float (&dx)[RB], const float (&dy)[RB],
-                                                  const float (&dz)[RB], int (&best)[RB], float (&bt)[RB], float (&bu)[RB],
-                                                  float (&bv)[RB]) {
-#pragma unroll
-  for (int k = 0; k < RB; k++) {
-    best[k] = -1;
-    bt[k] = 3.402823466e+38f;
-    bu[k] = 0.0f;
-    bv[k] = 0.0f;
-  }
+__device__ __forceinline__ void primary_triangles(const FastScene &sc, V3<float> d, int &best, float &bt, float &bu, float &bv) {
+  best = -1;
+  bt = 3.402823466e+38f;
+  bu = 0.0f;
+  bv = 0.0f;
   for (int l = 0; l < sc.n_prim; l++) {
     const int i = sc.plist[l];
     const float4 *q = sc.prim + 3 * i;
     const float4 PA = q[0], PB = q[1], PC = q[2];
-#pragma unroll
-    for (int k = 0; k < RB; k++) {
-      const float dn = (dx[k] * PA.x - dy[k] * PA.y) + dz[k] * PA.z;
-      const float E1 = (dx[k] * PB.x - dy[k] * PB.y) + dz[k] * PB.z;
-      const float E2 = (dx[k] * PC.x - dy[k] * PC.y) + dz[k] * PC.z;
-      const unsigned sb = __float_as_uint(dn) & 0x80000000u;
-      const float e1 = xor_sign(E1, sb), e2 = xor_sign(E2, sb), t0 = xor_sign(PA.w, sb), adn = fabsf(dn);
-      // u >= 0, v >= 0, u + v <= 1 (each widened by the tolerance) and t = det[b,e1,e2]/det A >= 0
-      if ((e1 >= -PB.w) & (e2 >= -PB.w) & ((e1 + e2) - adn <= PC.w) & (t0 <= 0.0f)) {
-        typedef sfloat S;
-        const V3<S> nd(S(-dx[k]), S(-dy[k]), S(-dz[k]));
-        const S detA = (nd.x * S(PA.x) - nd.y * S(PA.y)) + nd.z * S(PA.z);
-        const S inv = rcp_(detA);
-        const S t = S(PA.w) * inv;
-        const S u = ((nd.x * S(PB.x) - nd.y * S(PB.y)) + nd.z * S(PB.z)) * inv;
-        const S v = ((nd.x * S(PC.x) - nd.y * S(PC.y)) + nd.z * S(PC.z)) * inv;
-        if (t < S(bt[k]) && u >= S(0.0f) && v >= S(0.0f) && (u + v) <= S(1.0f) && t >= S(0.0f)) {
-          bt[k] = t.v;
-          best[k] = i;
-          bu[k] = u.v;
-          bv[k] = v.v;
-        }
+    const float dn = (d.x * PA.x - d.y * PA.y) + d.z * PA.z;
+    const float E1 = (d.x * PB.x - d.y * PB.y) + d.z * PB.z;
+    const float E2 = (d.x * PC.x - d.y * PC.y) + d.z * PC.z;
+    const unsigned sb = __float_as_uint(dn) & 0x80000000u;
+    const float e1 = xor_sign(E1, sb), e2 = xor_sign(E2, sb), t0 = xor_sign(PA.w, sb), adn = fabsf(dn);
+    // u >= 0, v >= 0, u + v <= 1 (each widened by the tolerance) and t = det[b,e1,e2]/det A >= 0
+    if ((e1 >= -PB.w) & (e2 >= -PB.w) & ((e1 + e2) - adn <= PC.w) & (t0 <= 0.0f)) {
+      typedef sfloat S;
+      const V3<S> nd(S(-d.x), S(-d.y), S(-d.z));
+      const S detA = (nd.x * S(PA.x) - nd.y * S(PA.y)) + nd.z * S(PA.z);
+      const S inv = rcp_(detA);
+      const S t = S(PA.w) * inv;
+      const S u = ((nd.x * S(PB.x) - nd.y * S(PB.y)) + nd.z * S(PB.z)) * inv;
+      const S v = ((nd.x * S(PC.x) - nd.y * S(PC.y)) + nd.z * S(PC.z)) * inv;
+      if (t < S(bt) && u >= S(0.0f) && v >= S(0.0f) && (u + v) <= S(1.0f) && t >= S(0.0f)) {
+        bt = t.v;
+        best = i;
+        bu = u.v;
+        bv = v.v;
       }
     }
   }
 }
 
 // The S jitters of a pixel: they depend on the pixel id only (kernels.cl:319,331).
-template <int CH> struct Jitters {
+template <int CH> struct Jitters {  // in registers
   float x[CH], y[CH], z[CH];
+  __device__ __forceinline__ float jx(int k) const { return x[k]; }
+  __device__ __forceinline__ float jy(int k) const { return y[k]; }
+  __device__ __forceinline__ float jz(int k) const { return z[k]; }
+};
+// The same in shared memory, component-major with a stride of one block so that the threads of a
+// warp read consecutive words: the jitters are only touched once per shading point (|d_k|^2) and by
+// the few (point, triangle) pairs that survive the culls, so they need not occupy 3*CH registers.
+template <int CH, int STRIDE> struct JittersShared {
+  float *p;  // this thread's column
+  __device__ __forceinline__ float jx(int k) const { return p[(3 * k + 0) * STRIDE]; }
+  __device__ __forceinline__ float jy(int k) const { return p[(3 * k + 1) * STRIDE]; }
+  __device__ __forceinline__ float jz(int k) const { return p[(3 * k + 2) * STRIDE]; }
+  __device__ __forceinline__ void store(const Jitters<CH> &j) const {
+#pragma unroll
+    for (int k = 0; k < CH; k++) {
+      p[(3 * k + 0) * STRIDE] = j.x[k];
+      p[(3 * k + 1) * STRIDE] = j.y[k];
+      p[(3 * k + 2) * STRIDE] = j.z[k];
+    }
+  }
 };
 
 __device__ __forceinline__ void seed_rng(int global_id, uint32_t &rx, uint32_t &ry, uint32_t &rz) {
@@ -179,15 +190,15 @@ __device__ __forceinline__ void make_jitters(uint32_t &rx, uint32_t &ry, uint32_
 
 // Number of UNOCCLUDED samples among the CH shadow rays start + t (r + j_k)  (in_shadow, kernels.cl:243-311).
 // The directions d_k = r + j_k are never materialised: d_k.X = r.X + j_k.X with r.X once per (point, triangle).
-template <int CH>
+template <int CH, class J>
 __device__ __forceinline__ int shadow_lit_count(const FastScene &sc, V3<float> start, V3<float> r, float radius_sq,
-                                                const Jitters<CH> &j, unsigned valid_mask) {
+                                                const J &j, unsigned valid_mask) {
   constexpr unsigned FULL = (CH >= 32) ? 0xffffffffu : ((1u << CH) - 1u);
   unsigned occ = ~valid_mask & FULL;  // padding samples of a ragged chunk count as occluded (ignored by the caller)
   float dd[CH];                       // |d_k|^2
 #pragma unroll
   for (int k = 0; k < CH; k++) {
-    const float ddx = r.x + j.x[k], ddy = r.y + j.y[k], ddz = r.z + j.z[k];
+    const float ddx = r.x + j.jx(k), ddy = r.y + j.jy(k), ddz = r.z + j.jz(k);
     dd[k] = (ddx * ddx + ddy * ddy) + ddz * ddz;
   }
   // |r| / |d_s| <= R / (R - jmax); no bound (k huge) when the light is closer than 2 jmax
@@ -224,9 +235,10 @@ __device__ __forceinline__ int shadow_lit_count(const FastScene &sc, V3<float> s
 #pragma unroll
     for (int k = 0; k < CH; k++) {
       // det A = -dn;  t = -num/dn;  u = E1/dn;  v = E2/dn
-      const float dn = fmaf(j.x[k], c0, fmaf(-j.y[k], c1, fmaf(j.z[k], c2, rN)));
-      const float E1 = fmaf(j.x[k], U.x, fmaf(j.y[k], U.y, fmaf(j.z[k], U.z, rU)));
-      const float E2 = fmaf(j.x[k], V.x, fmaf(j.y[k], V.y, fmaf(j.z[k], V.z, rV)));
+      const float jx = j.jx(k), jy = j.jy(k), jz = j.jz(k);
+      const float dn = fmaf(jx, c0, fmaf(-jy, c1, fmaf(jz, c2, rN)));
+      const float E1 = fmaf(jx, U.x, fmaf(jy, U.y, fmaf(jz, U.z, rU)));
+      const float E2 = fmaf(jx, V.x, fmaf(jy, V.y, fmaf(jz, V.z, rV)));
       // sign bit of sx clear  <=>  sign(E1) == sign(dn) && sign(E2) == sign(dn) && sign(num) != sign(dn)
       //                       <=>  u >= 0 && v >= 0 && t >= 0   (exact zeros aside)
       const unsigned dnb = __float_as_uint(dn);
@@ -253,7 +265,7 @@ __device__ __forceinline__ int shadow_lit_count(const FastScene &sc, V3<float> s
     for (int k = 0; k < CH; k++) {
       if ((occ >> k) & 1u) continue;
       const float a = dd[k];
-      const float b = 2.0f * fmaf(j.x[k], L.x, fmaf(j.y[k], L.y, fmaf(j.z[k], L.z, Lr)));
+      const float b = 2.0f * fmaf(j.jx(k), L.x, fmaf(j.jy(k), L.y, fmaf(j.jz(k), L.z, Lr)));
       const float disc = b * b - 4.0f * a * c;
       if (disc < 0.0f) continue;
       const float sq = sqrt_approx(disc);
@@ -270,16 +282,16 @@ __device__ __forceinline__ int shadow_lit_count(const FastScene &sc, V3<float> s
 
 // direct_light (kernels.cl:313-340) for one shading point.  SINGLE (S == CH): jit holds the pixel's
 // S jitters, generated once per pixel.  Otherwise they are regenerated chunk by chunk from the seed.
-template <int CH, bool SINGLE>
+template <int CH, bool SINGLE, class J>
 __device__ __forceinline__ float direct_light_fast(const FastScene &sc, V3<float> point, V3<float> normal, V3<float> light_pos, int S,
-                                                   int global_id, const Jitters<CH> &jit) {
+                                                   int global_id, const J &jit) {
   const V3<float> r = light_pos - point;
   const V3<float> start = point + scale(RT_BIAS, r);
   const float radius_sq = (r.x * r.x + r.y * r.y) + r.z * r.z;
   const float lam = RT_LIGHT_COLOR * fmaxf(dot(r, normal), 0.0f);
   int lit = 0;
   if constexpr (SINGLE) {
-    lit = shadow_lit_count<CH>(sc, start, r, radius_sq, jit, 0xffffffffu);
+    lit = shadow_lit_count<CH, J>(sc, start, r, radius_sq, jit, 0xffffffffu);
   } else {
     uint32_t rx, ry, rz;
     seed_rng(global_id, rx, ry, rz);
@@ -288,23 +300,10 @@ __device__ __forceinline__ float direct_light_fast(const FastScene &sc, V3<float
       Jitters<CH> jj;
       make_jitters<CH>(rx, ry, rz, jj);
       const unsigned valid = (s0 + CH > S) ? ((1u << (S - s0)) - 1u) : 0xffffffffu;
-      lit += shadow_lit_count<CH>(sc, start, r, radius_sq, jj, valid);
+      lit += shadow_lit_count<CH, Jitters<CH>>(sc, start, r, radius_sq, jj, valid);
     }
   }
   return (float)lit * lam * rcp_approx(4.0f * RT_PI_F * radius_sq * (float)S);
-}
-
-template <int N> __device__ __forceinline__ float sel(const float (&a)[N], int k) {
-  float r = a[0];
-#pragma unroll
-  for (int i = 1; i < N; i++) r = (k == i) ? a[i] : r;
-  return r;
-}
-template <int N> __device__ __forceinline__ int sel(const int (&a)[N], int k) {
-  int r = a[0];
-#pragma unroll
-  for (int i = 1; i < N; i++) r = (k == i) ? a[i] : r;
-  return r;
 }
 
 }  // namespace rt

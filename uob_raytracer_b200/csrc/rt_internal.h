@@ -27,6 +27,7 @@ struct rt_ctx {
   bool use_bvh = false;
   int sm_count = 0;
   uint64_t launches = 0;
+  size_t launch_extra_smem = 0;  // set by a launcher that needs shared memory beyond the scene
   std::string err;
 };
 

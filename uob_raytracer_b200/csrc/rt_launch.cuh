@@ -11,7 +11,7 @@ namespace rt {
 #define RT_THREADS 256
 #endif
 #ifndef RT_MINBLOCKS
-#define RT_MINBLOCKS 2
+#define RT_MINBLOCKS 3
 #endif
 constexpr int kThreads = RT_THREADS, kTileW = 16, kTileH = kThreads / 16;
 
@@ -40,9 +40,13 @@ __device__ __forceinline__ bool pixel_of_thread(const FrameParams &p, int &x, in
 }
 
 
+// float4 slots of the scene part of the fast kernel's shared memory (see brute_smem_bytes)
+__host__ __device__ inline int scene_smem_float4(int n, int n_sh) { return 8 * n + 4 * n_sh + (n + 3) / 4 + 1; }
+
 template <class K>
 inline cudaError_t launch_kernel(K kern, rt_ctx *ctx, const FrameParams &fp, cudaStream_t stream) {
-  const size_t smem = brute_smem_bytes(ctx->n, ctx->n_sh);
+  const size_t smem = brute_smem_bytes(ctx->n, ctx->n_sh) + ctx->launch_extra_smem;
+  ctx->launch_extra_smem = 0;
   if (smem > 48 * 1024) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
