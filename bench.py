@@ -192,30 +192,69 @@ def run_ours(args, cfg) -> int:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
     W, H = cfg.width, cfg.height
-    if H % world:
-        raise SystemExit(f"height {H} not divisible by {world} ranks")
-    rows = H // world
-    row0 = rank * rows
+    from uob_raytracer_b200 import tiles
+    row0, rows = tiles.row_tile(H, world, rank)
     counts = load_counts(cfg.name)
     scene, rot, cam4, light4 = scene_and_camera()
 
-    r = u.Renderer(W, H, cfg.aa, cfg.shadow_samples, cfg.max_bounces, device=local_rank, row0=row0, rows=rows)
-    r.upload_scene(scene)
-    frame = torch.zeros(H * W, dtype=torch.int32, device=f"cuda:{local_rank}")
-    tile = frame[row0 * W:(row0 + rows) * W]
-    host = torch.empty(H * W, dtype=torch.int32).pin_memory()
-    flush = torch.empty(256 << 20, dtype=torch.uint8, device=f"cuda:{local_rank}")  # > 126 MB L2
+    # Multi-GPU gather of the frame on rank 0:
+    #   nccl: contiguous row tiles, in-place NCCL all-gather into every rank's frame (the north-star path)
+    #   p2p : 16x16 blocks interleaved over the ranks (near-perfect balance), every rank's draw kernel
+    #         stores its pixels straight into rank 0's frame over NVLink (CUDA IPC mapping); the only
+    #         collective left is a 4-byte all-reduce that orders rank 0 after the peers' stores
+    gather = args.gather if world > 1 else "none"
+    if gather == "auto":
+        gather = "p2p"
     stream = torch.cuda.Stream(device=local_rank)  # a real (non-default) stream: the C ABI launches on it
     torch.cuda.set_stream(stream)
     sptr = stream.cuda_stream
     assert sptr != 0
+    frame = torch.zeros(H * W, dtype=torch.int32, device=f"cuda:{local_rank}")
+    tile = frame[row0 * W:(row0 + rows) * W]
+    host = torch.empty(H * W, dtype=torch.int32).pin_memory()
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=f"cuda:{local_rank}")  # > 126 MB L2
+    token = torch.zeros(1, dtype=torch.int32, device=f"cuda:{local_rank}")
+    peer_ptr = 0
+    if gather == "p2p":
+        r = u.Renderer(W, H, cfg.aa, cfg.shadow_samples, cfg.max_bounces, device=local_rank, block_stride=world,
+                       block_phase=rank)
+        handle = [r.ipc_export_frame() if rank == 0 else None]
+        dist.broadcast_object_list(handle, src=0)
+        target = r.device_frame_ptr if rank == 0 else r.ipc_open_frame(handle[0])
+        peer_ptr = 0 if rank == 0 else target
+    else:
+        r = u.Renderer(W, H, cfg.aa, cfg.shadow_samples, cfg.max_bounces, device=local_rank, row0=row0, rows=rows)
+        target = frame.data_ptr()
+    r.upload_scene(scene)
+    r.set_stream(sptr)
+
+    def render_only():
+        r.render_device(rot, cam4, light4, cfg.focal, dev_ptr=target, stream=sptr)
+
+    def gather_only():
+        if gather == "nccl":
+            dist.all_gather_into_tensor(frame, tile)
+        elif gather == "p2p":
+            dist.all_reduce(token)  # orders rank 0's next use of its frame after every peer's stores
 
     def step_device():
-        r.render_device(rot, cam4, light4, cfg.focal, dev_ptr=frame.data_ptr(), stream=sptr)
-        if dist is not None:
-            dist.all_gather_into_tensor(frame, tile)
+        render_only()
+        gather_only()
 
     fp32_peak = r.measure_fp32_peak() if rank == 0 else 0.0
+
+    # sanity (outside every timed region): the gathered frame on rank 0 has every pixel written
+    step_device()
+    torch.cuda.synchronize()
+    if rank == 0:
+        if gather == "p2p":
+            r.read_frame_host_ptr(host.data_ptr())
+        else:
+            host.copy_(frame)
+        torch.cuda.synchronize()
+        alpha = (host.numpy().view(np.uint32) >> 24)
+        if not (alpha == 255).all():
+            raise SystemExit(f"bench.py: gathered frame incomplete ({int((alpha != 255).sum())} pixels unwritten)")
 
     # ---- device-timed throughput ------------------------------------------------
     for _ in range(max(args.warmup, 3)):
@@ -234,10 +273,9 @@ def run_ours(args, cfg) -> int:
     for a, k, b in ev:
         flush.zero_()  # L2 flush between timed iterations; outside the event pair
         a.record(stream)
-        r.render_device(rot, cam4, light4, cfg.focal, dev_ptr=frame.data_ptr(), stream=sptr)
+        render_only()
         k.record(stream)
-        if dist is not None:
-            dist.all_gather_into_tensor(frame, tile)
+        gather_only()
         b.record(stream)
     torch.cuda.synchronize()
     t_wall = time.perf_counter() - t_wall0
@@ -268,10 +306,12 @@ def run_ours(args, cfg) -> int:
     else:
         # every rank: render tile -> all-gather -> rank 0 reads the whole frame back
         def step_e2e():
-            r.render_device(rot, cam4, light4, cfg.focal, dev_ptr=frame.data_ptr(), stream=sptr)
-            dist.all_gather_into_tensor(frame, tile)
+            step_device()
             if rank == 0:
-                host.copy_(frame, non_blocking=True)
+                if gather == "p2p":
+                    r.read_frame_host_ptr(host.data_ptr())  # D2H on the same stream, blocking
+                else:
+                    host.copy_(frame, non_blocking=True)
             torch.cuda.synchronize()
         for _ in range(3):
             step_e2e()
@@ -285,7 +325,7 @@ def run_ours(args, cfg) -> int:
         t_e2e = float(t_e2e.cpu())
         e2e_line = {"value": round(counts["rays"] / t_e2e / 1e6, 1), "unit": UNIT, "ms_per_step": round(t_e2e * 1e3, 4),
                     "h2d_bytes_per_step": 84, "d2h_bytes_per_step": W * H * 4,
-                    "api": "rt_render_device per rank + NCCL all-gather + read-back on rank 0"}
+                    "api": "rt_render_device per rank + " + ("NCCL all-gather" if gather == "nccl" else "peer stores into rank 0's frame + 4-byte all-reduce") + " + read-back on rank 0"}
 
     if rank == 0:
         ms_per_step = total_step_ms / args.steps
@@ -300,7 +340,9 @@ def run_ours(args, cfg) -> int:
             "config": {"workload": cfg.name, "description": cfg.description, "width": W, "height": H, "aa": cfg.aa,
                        "shadow_samples": cfg.shadow_samples, "max_bounces": cfg.max_bounces, "focal": cfg.focal,
                        "rays_per_frame": counts["rays"], "rays_source": "oracle counters (tests/golden/ray_counts.json)",
-                       "partition": f"{world} row tile(s) of {rows} rows" + (", in-place NCCL all-gather per frame" if world > 1 else ""),
+                       "partition": (f"{world} row tile(s) of {rows} rows" + (", in-place NCCL all-gather per frame" if world > 1 else ""))
+                       if gather != "p2p" else f"16x16-pixel blocks interleaved over {world} ranks, peer stores into rank 0's frame over NVLink + 4-byte all-reduce per frame",
+                       "gather": gather,
                        "l2": "flushed between timed iterations (256 MiB memset outside the timed event pairs); "
                              "the scene is 3.4 KB and lives in shared memory",
                        "arithmetic": "fast path (FMA, division-free shadow tests); RT_FLAG_STRICT_IEEE is the bit-exact anchor"},
@@ -333,6 +375,11 @@ def run_ours(args, cfg) -> int:
                           f", best of {i + 1} frames; verbatim kernels.cl via g++ shim (-O2, strict IEEE), all host threads",
                 "ms_per_frame": round(best * step * 1e3, 1)}
         print(json.dumps(line), flush=True)
+    if peer_ptr:
+        torch.cuda.synchronize()
+        r.ipc_close_frame(peer_ptr)
+    if dist is not None:
+        dist.barrier()
     r.close()
     if dist is not None:
         dist.barrier()
@@ -348,6 +395,8 @@ def main() -> int:
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
     ap.add_argument("--workload", default="cfg2")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--gather", choices=["auto", "nccl", "p2p"], default="auto",
+                    help="N>1: how the frame reaches rank 0 (auto = p2p)")
     args = ap.parse_args()
     import uob_raytracer_b200 as u
     cfg = u.CONFIGS[args.workload]

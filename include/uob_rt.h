@@ -57,6 +57,11 @@ typedef struct rt_config {
                          Pixel ids and ray directions stay frame-global, so N row tiles
                          concatenate to exactly the 1-GPU frame. */
   uint32_t flags;
+  /* Finer multi-GPU partition: the 16x16-pixel blocks of rows [row0,row0+rows) are numbered
+   * row-major and this context renders blocks block_phase, block_phase+block_stride, ... —
+   * rank g of N uses stride N, phase g; N interleaved contexts cover the rows exactly once
+   * with near-perfect load balance.  block_stride <= 1 = every block (plain row tile). */
+  int block_stride, block_phase;
 } rt_config;
 
 /* Defaults of the reference at HEAD: 1024x1024, aa 2, 10 shadow samples, 10 bounces, device 0. */
@@ -95,6 +100,11 @@ int rt_render(rt_ctx *ctx, const float rot12[12], const float cam[4], const floa
 int rt_render_device(rt_ctx *ctx, const float rot12[12], const float cam[4], const float light[4],
                      float focal_length, uint32_t *dev_argb, void *stream);
 
+/* Make `stream` (a cudaStream_t of the context's device) the context's stream for all later
+ * launches, copies and rt_synchronize; NULL restores the context's own stream.  Lets a host that
+ * already owns a stream (torch, a render loop with its own queue) keep everything in order. */
+int rt_set_stream(rt_ctx *ctx, void *stream);
+
 /* Wait for everything queued on the context's stream. */
 int rt_synchronize(rt_ctx *ctx);
 
@@ -121,6 +131,24 @@ const char *rt_last_error(const rt_ctx *ctx);
  * FFMA microbenchmark, best of 5, CUDA events) — the roofline denominator bench.py reports
  * the render kernel against.  Not part of the reference's surface. */
 int rt_measure_fp32_peak(rt_ctx *ctx, float *tflops);
+
+/* Multi-GPU without a collective: every rank writes its pixels straight into ONE rank's frame
+ * buffer over NVLink (peer-mapped stores from inside the draw kernel).
+ *   single process:  rt_enable_peer(ctx, peer_device) then pass the other context's
+ *                    rt_device_frame() as dev_argb of rt_render_device;
+ *   one process per GPU:  the owner exports its frame with rt_ipc_export_frame (64-byte CUDA IPC
+ *                    handle, to be sent to the peers by any means), the peers map it with
+ *                    rt_ipc_open_frame and pass the mapped pointer as dev_argb.
+ * Completion of the peers' stores is the caller's job (a stream/event wait in one process, any
+ * barrier enqueued after the kernel across processes). */
+int rt_enable_peer(rt_ctx *ctx, int peer_device);
+int rt_ipc_export_frame(rt_ctx *ctx, void *handle64);
+int rt_ipc_open_frame(rt_ctx *ctx, const void *handle64, uint32_t **dev_argb);
+int rt_ipc_close_frame(rt_ctx *ctx, uint32_t *dev_argb);
+
+/* Blocking read-back of the WHOLE frame buffer of this context (width*height uint32) — what the
+ * owner of a peer-written frame calls once the peers are done. */
+int rt_read_frame(rt_ctx *ctx, uint32_t *host_argb);
 
 /* Library version string, e.g. "uob_rt 0.1 (sm_100a)". */
 const char *rt_version(void);

@@ -29,7 +29,8 @@ class RtConfig(ctypes.Structure):
     """struct rt_config of include/uob_rt.h."""
     _fields_ = [("width", ctypes.c_int), ("height", ctypes.c_int), ("aa", ctypes.c_int),
                 ("shadow_samples", ctypes.c_int), ("max_bounces", ctypes.c_int), ("device", ctypes.c_int),
-                ("row0", ctypes.c_int), ("rows", ctypes.c_int), ("flags", ctypes.c_uint32)]
+                ("row0", ctypes.c_int), ("rows", ctypes.c_int), ("flags", ctypes.c_uint32),
+                ("block_stride", ctypes.c_int), ("block_phase", ctypes.c_int)]
 
 
 # every symbol include/uob_rt.h declares: name -> (restype, argtypes)
@@ -40,6 +41,7 @@ RT_SYMBOLS = {
     "rt_render": (ctypes.c_int, [ctypes.c_void_p, c_float_p, c_float_p, c_float_p, ctypes.c_float, ctypes.c_void_p]),
     "rt_render_device": (ctypes.c_int, [ctypes.c_void_p, c_float_p, c_float_p, c_float_p, ctypes.c_float,
                                         ctypes.c_void_p, ctypes.c_void_p]),
+    "rt_set_stream": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p]),
     "rt_synchronize": (ctypes.c_int, [ctypes.c_void_p]),
     "rt_device_frame": (ctypes.c_void_p, [ctypes.c_void_p]),
     "rt_last_kernel_ms": (ctypes.c_float, [ctypes.c_void_p]),
@@ -48,6 +50,11 @@ RT_SYMBOLS = {
     "rt_destroy": (None, [ctypes.c_void_p]),
     "rt_last_error": (ctypes.c_char_p, [ctypes.c_void_p]),
     "rt_measure_fp32_peak": (ctypes.c_int, [ctypes.c_void_p, c_float_p]),
+    "rt_enable_peer": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int]),
+    "rt_ipc_export_frame": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p]),
+    "rt_ipc_open_frame": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.POINTER(ctypes.c_void_p)]),
+    "rt_ipc_close_frame": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p]),
+    "rt_read_frame": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p]),
     "rt_version": (ctypes.c_char_p, []),
 }
 

@@ -43,11 +43,12 @@ static int free_ctx(rt_ctx *ctx) {
   if (!ctx) return RT_OK;
   cudaSetDevice(ctx->cfg.device);
   if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+  if (ctx->own_stream && ctx->own_stream != ctx->stream) cudaStreamSynchronize(ctx->own_stream);
   if (ctx->d_frame) cudaFree(ctx->d_frame);
   if (ctx->d_scene) cudaFree(ctx->d_scene);
   if (ctx->ev0) cudaEventDestroy(ctx->ev0);
   if (ctx->ev1) cudaEventDestroy(ctx->ev1);
-  if (ctx->stream) cudaStreamDestroy(ctx->stream);
+  if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
   delete ctx;
   return RT_OK;
 }
@@ -83,6 +84,11 @@ rt_ctx *rt_create(const rt_config *cfg) {
   ctx->cfg = *cfg;
   ctx->row0 = cfg->rows > 0 ? cfg->row0 : 0;
   ctx->rows = cfg->rows > 0 ? cfg->rows : cfg->height;
+  if (cfg->block_stride > 1 && (cfg->block_phase < 0 || cfg->block_phase >= cfg->block_stride)) {
+    g_create_err = "rt_create: block_phase must be in [0, block_stride)";
+    delete ctx;
+    return nullptr;
+  }
   if (ctx->row0 < 0 || ctx->row0 + ctx->rows > cfg->height) {
     g_create_err = "rt_create: row tile outside the frame";
     delete ctx;
@@ -97,7 +103,8 @@ rt_ctx *rt_create(const rt_config *cfg) {
   cudaDeviceProp prop;
   if ((e = cudaGetDeviceProperties(&prop, cfg->device)) != cudaSuccess) return fail("querying device", e);
   ctx->sm_count = prop.multiProcessorCount;
-  if ((e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)) != cudaSuccess) return fail("creating stream", e);
+  if ((e = cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking)) != cudaSuccess) return fail("creating stream", e);
+  ctx->stream = ctx->own_stream;
   if ((e = cudaEventCreate(&ctx->ev0)) != cudaSuccess) return fail("creating event", e);
   if ((e = cudaEventCreate(&ctx->ev1)) != cudaSuccess) return fail("creating event", e);
   if ((e = cudaMalloc(&ctx->d_frame, sizeof(uint32_t) * (size_t)cfg->width * cfg->height)) != cudaSuccess)
@@ -233,6 +240,71 @@ int rt_render(rt_ctx *ctx, const float rot12[12], const float cam[4], const floa
   RT_CUDA(ctx, cudaMemcpyAsync(host_argb, ctx->d_frame + off, sizeof(uint32_t) * cnt, cudaMemcpyDeviceToHost, ctx->stream),
           "reading screen buffer data");
   RT_CUDA(ctx, cudaStreamSynchronize(ctx->stream), "reading screen buffer data");
+  return RT_OK;
+}
+
+int rt_read_frame(rt_ctx *ctx, uint32_t *host_argb) {
+  if (!ctx || !host_argb) return RT_ERR_INVALID;
+  RT_CUDA(ctx, cudaSetDevice(ctx->cfg.device), "selecting device");
+  RT_CUDA(ctx, cudaMemcpyAsync(host_argb, ctx->d_frame, sizeof(uint32_t) * (size_t)ctx->cfg.width * ctx->cfg.height,
+                               cudaMemcpyDeviceToHost, ctx->stream), "reading screen buffer data");
+  RT_CUDA(ctx, cudaStreamSynchronize(ctx->stream), "reading screen buffer data");
+  return RT_OK;
+}
+
+int rt_enable_peer(rt_ctx *ctx, int peer_device) {
+  if (!ctx) return RT_ERR_INVALID;
+  RT_CUDA(ctx, cudaSetDevice(ctx->cfg.device), "selecting device");
+  if (peer_device == ctx->cfg.device) return RT_OK;
+  int can = 0;
+  RT_CUDA(ctx, cudaDeviceCanAccessPeer(&can, ctx->cfg.device, peer_device), "querying peer access");
+  if (!can) {
+    ctx->err = "rt_enable_peer: device cannot access the peer";
+    return RT_ERR_CUDA;
+  }
+  cudaError_t e = cudaDeviceEnablePeerAccess(peer_device, 0);
+  if (e == cudaErrorPeerAccessAlreadyEnabled) {
+    cudaGetLastError();
+    return RT_OK;
+  }
+  RT_CUDA(ctx, e, "enabling peer access");
+  return RT_OK;
+}
+
+int rt_ipc_export_frame(rt_ctx *ctx, void *handle64) {
+  if (!ctx || !handle64) return RT_ERR_INVALID;
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "CUDA IPC handle size");
+  RT_CUDA(ctx, cudaSetDevice(ctx->cfg.device), "selecting device");
+  cudaIpcMemHandle_t h;
+  RT_CUDA(ctx, cudaIpcGetMemHandle(&h, ctx->d_frame), "exporting the frame buffer");
+  memcpy(handle64, &h, sizeof h);
+  return RT_OK;
+}
+
+int rt_ipc_open_frame(rt_ctx *ctx, const void *handle64, uint32_t **dev_argb) {
+  if (!ctx || !handle64 || !dev_argb) return RT_ERR_INVALID;
+  RT_CUDA(ctx, cudaSetDevice(ctx->cfg.device), "selecting device");
+  cudaIpcMemHandle_t h;
+  memcpy(&h, handle64, sizeof h);
+  void *p = nullptr;
+  RT_CUDA(ctx, cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess), "mapping the peer frame buffer");
+  *dev_argb = static_cast<uint32_t *>(p);
+  return RT_OK;
+}
+
+int rt_ipc_close_frame(rt_ctx *ctx, uint32_t *dev_argb) {
+  if (!ctx || !dev_argb) return RT_ERR_INVALID;
+  RT_CUDA(ctx, cudaSetDevice(ctx->cfg.device), "selecting device");
+  RT_CUDA(ctx, cudaStreamSynchronize(ctx->stream), "waiting for the stream");
+  RT_CUDA(ctx, cudaIpcCloseMemHandle(dev_argb), "unmapping the peer frame buffer");
+  return RT_OK;
+}
+
+int rt_set_stream(rt_ctx *ctx, void *stream) {
+  if (!ctx) return RT_ERR_INVALID;
+  RT_CUDA(ctx, cudaSetDevice(ctx->cfg.device), "selecting device");
+  RT_CUDA(ctx, cudaStreamSynchronize(ctx->stream), "waiting for the stream");
+  ctx->stream = stream ? static_cast<cudaStream_t>(stream) : ctx->own_stream;
   return RT_OK;
 }
 

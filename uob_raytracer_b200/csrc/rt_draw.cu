@@ -17,8 +17,8 @@ __global__ void __launch_bounds__(kThreads) draw_brute_kernel(const __grid_const
   extern __shared__ float4 smem[];
   const SceneView sc = stage_scene(smem, scene, n, n_sh);
   __syncthreads();
-  int x, y;
-  if (!pixel_of_thread(p, x, y)) return;
+  int x, y, tx, ty;
+  if (!pixel_of_thread(p, x, y, tx, ty)) return;
   p.out[(size_t)y * p.W + x] = shade_pixel<T, CH>(sc, p, x, y);
 }
 

@@ -42,13 +42,15 @@ __global__ void __launch_bounds__(kThreads, RT_MINBLOCKS) draw_fast_kernel(const
   const V3<float> cam(p.cam[0], p.cam[1], p.cam[2]), light(p.light[0], p.light[1], p.light[2]);
   const int A = p.A, S = p.S;
   const float SW = (float)p.W, SH = (float)p.H, fA = (float)A;
+  int x, y, tile_x, tile_y;
+  const bool in_frame = pixel_of_thread(p, x, y, tile_x, tile_y);
   __syncthreads();
 
   // ---- per-triangle camera constants + binning of the triangles against this block's tile ----
   {
     // corner rays of the tile in virtual (sub-pixel) coordinates, un-normalised (kernels.cl:384-400)
-    const float vx0 = (float)(blockIdx.x * kTileW * A) - SW * fA * 0.5f;
-    const float vy0 = (float)((p.row0 + blockIdx.y * kTileH) * A) - SH * fA * 0.5f;
+    const float vx0 = (float)(tile_x * A) - SW * fA * 0.5f;
+    const float vy0 = (float)(tile_y * A) - SH * fA * 0.5f;
     const float vx1 = vx0 + (float)(kTileW * A - 1), vy1 = vy0 + (float)(kTileH * A - 1);
     V3<float> dc[4];
     float dmax = 0.0f;
@@ -114,8 +116,7 @@ __global__ void __launch_bounds__(kThreads, RT_MINBLOCKS) draw_fast_kernel(const
   }
   const bool spheres_visible = s_spheres_visible != 0;
 
-  int x, y;
-  if (!pixel_of_thread(p, x, y)) return;
+  if (!in_frame) return;
 
   const int global_id = __float2int_rz(__fadd_rn(__fmul_rn((float)y, SW), (float)x));  // kernels.cl:380, float arithmetic
   // SINGLE: the pixel's S jitters, generated on the first shading point (44 % of the 1080p frame

@@ -15,7 +15,8 @@ struct FrameParams;
 struct rt_ctx {
   rt_config cfg{};
   int row0 = 0, rows = 0;  // resolved tile
-  cudaStream_t stream = nullptr;
+  cudaStream_t stream = nullptr;      // the stream in use
+  cudaStream_t own_stream = nullptr;  // created by rt_create
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   bool timed = false;
   uint32_t *d_frame = nullptr;  // whole frame, W*H

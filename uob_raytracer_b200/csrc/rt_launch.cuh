@@ -32,10 +32,15 @@ __device__ __forceinline__ SceneView stage_scene(float4 *smem, const float4 *__r
   return sc;
 }
 
-__device__ __forceinline__ bool pixel_of_thread(const FrameParams &p, int &x, int &y) {
+// Pixel tile of this block (top-left corner) and pixel of this thread; false if outside the frame rows.
+__device__ __forceinline__ bool pixel_of_thread(const FrameParams &p, int &x, int &y, int &tile_x, int &tile_y) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  x = blockIdx.x * kTileW + (warp & 1) * 8 + (lane & 7);
-  y = p.row0 + blockIdx.y * kTileH + (warp >> 1) * 4 + (lane >> 3);
+  const int gb = blockIdx.x * p.blk_stride + p.blk_phase;
+  const int by = gb / p.grid_x, bx = gb - by * p.grid_x;
+  tile_x = bx * kTileW;
+  tile_y = p.row0 + by * kTileH;
+  x = tile_x + (warp & 1) * 8 + (lane & 7);
+  y = tile_y + (warp >> 1) * 4 + (lane >> 3);
   return x < p.W && y < p.row0 + p.rows;
 }
 
@@ -44,15 +49,21 @@ __device__ __forceinline__ bool pixel_of_thread(const FrameParams &p, int &x, in
 __host__ __device__ inline int scene_smem_float4(int n, int n_sh) { return 8 * n + 4 * n_sh + (n + 3) / 4 + 1; }
 
 template <class K>
-inline cudaError_t launch_kernel(K kern, rt_ctx *ctx, const FrameParams &fp, cudaStream_t stream) {
+inline cudaError_t launch_kernel(K kern, rt_ctx *ctx, const FrameParams &fp_in, cudaStream_t stream) {
+  FrameParams fp = fp_in;
+  fp.grid_x = (fp.W + kTileW - 1) / kTileW;
+  fp.n_blocks = fp.grid_x * ((fp.rows + kTileH - 1) / kTileH);
+  fp.blk_stride = ctx->cfg.block_stride > 1 ? ctx->cfg.block_stride : 1;
+  fp.blk_phase = ctx->cfg.block_stride > 1 ? ctx->cfg.block_phase : 0;
+  const int my_blocks = (fp.n_blocks - fp.blk_phase + fp.blk_stride - 1) / fp.blk_stride;
   const size_t smem = brute_smem_bytes(ctx->n, ctx->n_sh) + ctx->launch_extra_smem;
   ctx->launch_extra_smem = 0;
   if (smem > 48 * 1024) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
   }
-  dim3 grid((fp.W + kTileW - 1) / kTileW, (fp.rows + kTileH - 1) / kTileH);
-  kern<<<grid, kThreads, smem, stream>>>(fp, ctx->d_scene, ctx->n, ctx->n_sh);
+  if (my_blocks <= 0) return cudaSuccess;
+  kern<<<my_blocks, kThreads, smem, stream>>>(fp, ctx->d_scene, ctx->n, ctx->n_sh);
   ctx->launches++;
   return cudaGetLastError();
 }

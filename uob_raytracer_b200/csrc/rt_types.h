@@ -10,6 +10,9 @@ namespace rt {
 struct FrameParams {
   int W, H;        // whole frame
   int row0, rows;  // rows rendered by this launch
+  // 16 x kTileH pixel blocks of those rows are numbered row-major; this launch renders the blocks
+  // gb = b*blk_stride + blk_phase (b = blockIdx.x): 1/0 = all of them, N/g = rank g of an N-way interleave
+  int blk_stride, blk_phase, grid_x, n_blocks;
   int A, S, B;     // AA edge, shadow samples, max bounces
   float focal;
   float rot[9];    // rows r0, r1, r2 (skeleton.cpp:149-151)

@@ -31,11 +31,11 @@ def _f32(a, n: int) -> np.ndarray:
 class Renderer:
     def __init__(self, width: int = 1024, height: int = 1024, aa: int = 2, shadow_samples: int = 10,
                  max_bounces: int = 10, device: int = 0, row0: int = 0, rows: int = 0, strict: bool = False,
-                 force_bvh: bool = False, force_brute: bool = False):
+                 force_bvh: bool = False, force_brute: bool = False, block_stride: int = 0, block_phase: int = 0):
         self._lib = rt_lib()
         flags = (RT_FLAG_STRICT_IEEE if strict else 0) | (RT_FLAG_FORCE_BVH if force_bvh else 0) | \
                 (RT_FLAG_FORCE_BRUTE if force_brute else 0)
-        self.cfg = RtConfig(width, height, aa, shadow_samples, max_bounces, device, row0, rows, flags)
+        self.cfg = RtConfig(width, height, aa, shadow_samples, max_bounces, device, row0, rows, flags, block_stride, block_phase)
         self._ctx = self._lib.rt_create(ctypes.byref(self.cfg))
         if not self._ctx:
             raise RtError(self._lib.rt_last_error(None).decode())
@@ -102,6 +102,37 @@ class Renderer:
         self._check(self._lib.rt_render_device(self._ctx, rot12.ctypes.data_as(c_float_p),
                                                cam4.ctypes.data_as(c_float_p), light4.ctypes.data_as(c_float_p), focal,
                                                dev_ptr or None, stream or None))
+
+    # -- peer-written frames (multi-GPU without a collective) -----------------
+    def read_frame(self, out: np.ndarray | None = None) -> np.ndarray:
+        """Blocking read-back of the context's whole frame buffer."""
+        if out is None:
+            out = np.empty((self.height, self.width), np.uint32)
+        self._check(self._lib.rt_read_frame(self._ctx, out.ctypes.data))
+        return out
+
+    def read_frame_host_ptr(self, host_ptr: int) -> None:
+        self._check(self._lib.rt_read_frame(self._ctx, host_ptr))
+
+    def enable_peer(self, peer_device: int) -> None:
+        self._check(self._lib.rt_enable_peer(self._ctx, peer_device))
+
+    def ipc_export_frame(self) -> bytes:
+        buf = ctypes.create_string_buffer(64)
+        self._check(self._lib.rt_ipc_export_frame(self._ctx, buf))
+        return buf.raw
+
+    def ipc_open_frame(self, handle: bytes) -> int:
+        out = ctypes.c_void_p()
+        self._check(self._lib.rt_ipc_open_frame(self._ctx, ctypes.c_char_p(handle), ctypes.byref(out)))
+        return int(out.value)
+
+    def ipc_close_frame(self, dev_ptr: int) -> None:
+        self._check(self._lib.rt_ipc_close_frame(self._ctx, dev_ptr))
+
+    def set_stream(self, stream: int) -> None:
+        """Use the caller's cudaStream_t (0 = back to the context's own) for everything that follows."""
+        self._check(self._lib.rt_set_stream(self._ctx, stream or None))
 
     def synchronize(self) -> None:
         self._check(self._lib.rt_synchronize(self._ctx))
