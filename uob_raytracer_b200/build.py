@@ -16,7 +16,7 @@ HOST_LIB = os.path.join(PKG, "libuob_host.so")
 HOST_SOURCES = [os.path.join("host", "uob_host.cpp")]
 HOST_FLAGS = ["-std=c++17", "-O2", "-ffp-contract=off", "-fno-fast-math", "-fPIC", "-shared", "-Wall"]
 
-SOURCES = ["rt_api.cu", "rt_draw.cu", "rt_peak.cu"]
+SOURCES = ["rt_api.cu", "rt_draw.cu", "rt_peak.cu", "rt_bvh.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "-Xcompiler", "-fPIC,-ffp-contract=off,-fno-fast-math", "--expt-relaxed-constexpr",

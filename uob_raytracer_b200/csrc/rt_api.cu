@@ -46,6 +46,7 @@ static int free_ctx(rt_ctx *ctx) {
   if (ctx->own_stream && ctx->own_stream != ctx->stream) cudaStreamSynchronize(ctx->own_stream);
   if (ctx->d_frame) cudaFree(ctx->d_frame);
   if (ctx->d_scene) cudaFree(ctx->d_scene);
+  rt::bvh_free(ctx);
   if (ctx->ev0) cudaEventDestroy(ctx->ev0);
   if (ctx->ev1) cudaEventDestroy(ctx->ev1);
   if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
@@ -135,9 +136,16 @@ int rt_upload_scene(rt_ctx *ctx, const float *verts, const float *normals, const
     return RT_ERR_INVALID;
   }
   if (use_bvh) {
-    ctx->err = "rt_upload_scene: BVH path not built yet";
-    return RT_ERR_INVALID;
+    // Large meshes: GPU-built LBVH over float4 SoA buffers in HBM (rt_bvh.cu)
+    RT_CUDA(ctx, cudaStreamSynchronize(ctx->stream), "waiting before scene replacement");
+    RT_CUDA(ctx, rt::bvh_build(ctx, verts, normals, colors, n), "building the BVH");
+    ctx->n = n;
+    ctx->n_sh = n_sh;
+    ctx->use_bvh = true;
+    ctx->have_scene = true;
+    return RT_OK;
   }
+  rt::bvh_free(ctx);
   // Per-triangle constants, computed with the single-rounded operations the
   // reference kernel performs per ray (kernels.cl:102-104 and the cofactors of
   // det, :31-35).  volatile keeps the host compiler from contracting a*b-c*d.
@@ -216,7 +224,7 @@ static int render_impl(rt_ctx *ctx, const float rot12[12], const float cam[4], c
   }
   fp.out = dev_argb ? dev_argb : ctx->d_frame;
   RT_CUDA(ctx, cudaEventRecord(ctx->ev0, stream), "recording start event");
-  RT_CUDA(ctx, rt::launch_draw_brute(ctx, fp, stream), "enqueueing draw kernel");
+  RT_CUDA(ctx, ctx->use_bvh ? rt::launch_draw_bvh(ctx, fp, stream) : rt::launch_draw_brute(ctx, fp, stream), "enqueueing draw kernel");
   RT_CUDA(ctx, cudaEventRecord(ctx->ev1, stream), "recording stop event");
   ctx->timed = true;
   return RT_OK;

@@ -1,16 +1,22 @@
-// rt_brute.cuh — brute-force render path (small scenes staged in shared memory).
+// rt_brute.cuh — the generic render path: device equivalents of the helpers of
+// Source/kernels.cl, written once for both arithmetic policies (rt_math.cuh) and
+// for both ways of finding candidate triangles (a Tracer: brute force over a
+// small scene in shared memory here, BVH traversal in rt_bvh.cuh).
 //
-// Device equivalents of the helpers of Source/kernels.cl, written once for both
-// arithmetic policies (rt_math.cuh).  What differs from the reference's loop
-// structure, and why it does not change results:
+// What differs from the reference's loop structure, and why it does not change
+// results:
 //   * per-triangle constants (e1 = v1-v0, e2 = v2-v0 and the three cofactors of
 //     the first row of det[., e1, e2]) are precomputed at upload with the same
-//     single-rounded operations the kernel would perform (rt_scene.cu);
+//     single-rounded operations the kernel would perform (rt_api.cu);
 //   * the any-hit loop (in_shadow, kernels.cl:243-311) runs triangle-outer /
 //     shadow-sample-inner: everything that depends only on (start, triangle) —
 //     b, det[b,e1,e2] and the cofactors of det[-d,b,e2], det[-d,e1,b] — is
 //     computed once per triangle instead of once per sample.  in_shadow returns
 //     a boolean OR over occluders, so the order of evaluation is immaterial;
+//   * closest hit keeps (t, u, v, index) of the winner and forms the hit point
+//     after the loop; with a BVH the triangles arrive in arbitrary order, so the
+//     reference's "strict <, ascending index" rule (lowest index wins an exact tie)
+//     is applied explicitly;
 //   * the fast policy decides t >= 0, |t d|^2 < r^2, u >= 0, v >= 0, u+v <= 1
 //     without dividing (the sign of det A is carried instead).
 #pragma once
@@ -32,10 +38,11 @@ static __constant__ float4 c_sphere_color[RT_SPHERES] = {{0.0f, 0.0f, 0.0f, -1.0
 #define RT_LIGHT_COLOR 16.0f
 #define RT_LIGHT_SPREAD 0.05f
 #define RT_PI_F 3.14159265358979323846f
+#define RT_MAXFLOAT 3.402823466e+38f
 
-// Scene as the kernels read it.  Closest-hit arrays hold all n triangles in
-// upload order; the shadow arrays hold only shadow casters (material != -1,
-// kernels.cl:247), also in upload order.
+// Scene as the brute-force kernels read it.  Closest-hit arrays hold all n
+// triangles in upload order; the shadow arrays hold only shadow casters
+// (material != -1, kernels.cl:247), also in upload order.
 //   ta[i] = (v0.xyz, c0)   tb[i] = (e1.xyz, c1)   tc[i] = (e2.xyz, c2)
 //   with c0 = e1.y*e2.z - e1.z*e2.y, c1 = e1.x*e2.z - e1.z*e2.x, c2 = e1.x*e2.y - e1.y*e2.x
 //   so that det[m, e1, e2] = (m.x*c0 - m.y*c1) + m.z*c2   (kernels.cl:31-35)
@@ -51,6 +58,48 @@ template <class T> struct HitRec {
   V3<T> point, normal;
   float4 color;
 };
+
+// Running state of a closest-hit search over triangles.
+template <class T> struct ClosestState {
+  T t, u, v;
+  int id;     // index in the caller's numbering (upload order), -1 = none
+  int slot;   // where the caller finds the winner's data (== id for brute force)
+  __device__ __forceinline__ void reset() {
+    t = T(RT_MAXFLOAT);
+    u = T(0.0f);
+    v = T(0.0f);
+    id = -1;
+    slot = -1;
+  }
+};
+
+// One ray/triangle test of the closest-hit search (kernels.cl:102-128).  `ordered`: the caller
+// visits triangles in ascending index, so `t < current` alone implements the tie rule.
+template <class T, bool ORDERED>
+__device__ __forceinline__ void closest_tri_test(float4 A, float4 Bq, float4 C, V3<T> start, V3<T> nd, int id, int slot,
+                                                 ClosestState<T> &cs) {
+  const V3<T> v0 = xyz<T>(A), e1 = xyz<T>(Bq), e2 = xyz<T>(C);
+  const T c0 = T(A.w), c1 = T(Bq.w), c2 = T(C.w);
+  const V3<T> b = start - v0;
+  const T detA = (nd.x * c0 - nd.y * c1) + nd.z * c2;
+  const T inv = rcp_(detA);
+  const T t = ((b.x * c0 - b.y * c1) + b.z * c2) * inv;
+  const T u = ((nd.x * (b.y * e2.z - b.z * e2.y) - nd.y * (b.x * e2.z - b.z * e2.x)) + nd.z * (b.x * e2.y - b.y * e2.x)) * inv;
+  const T v = ((nd.x * (e1.y * b.z - e1.z * b.y) - nd.y * (e1.x * b.z - e1.z * b.x)) + nd.z * (e1.x * b.y - e1.y * b.x)) * inv;
+  const bool closer = ORDERED ? (t < cs.t) : ((t < cs.t) || (t == cs.t && id < cs.id));
+  if (closer && u >= T(0.0f) && v >= T(0.0f) && (u + v) <= T(1.0f) && t >= T(0.0f)) {
+    cs.id = id;
+    cs.slot = slot;
+    cs.u = u;
+    cs.v = v;
+    cs.t = t;
+  }
+}
+
+// (v0 + u*e1) + v*e2 of the winning triangle (kernels.cl:124)
+template <class T> __device__ __forceinline__ V3<T> hit_point(float4 A, float4 Bq, float4 C, T u, T v) {
+  return (xyz<T>(A) + scale(u, xyz<T>(Bq))) + scale(v, xyz<T>(C));
+}
 
 // Sphere part of the closest-hit search (kernels.cl:132-163), continuing from current_t.
 template <class T>
@@ -83,99 +132,66 @@ __device__ __forceinline__ void closest_spheres(V3<T> start, V3<T> dir, T curren
   }
 }
 
-// ---------------------------------------------------------------------------
-// Closest hit: kernels.cl:92-166 / :168-241.
-// ---------------------------------------------------------------------------
-template <class T>
-__device__ __forceinline__ void closest_hit(const SceneView &sc, V3<T> start, V3<T> dir, HitRec<T> &hit) {
-  T current_t = T(3.402823466e+38f);  // MAXFLOAT
-  const V3<T> nd = -dir;
-  int best = -1;
-  T best_u = T(0.0f), best_v = T(0.0f);
-  for (int i = 0; i < sc.n; i++) {
-    const float4 A = sc.ta[i], Bq = sc.tb[i], C = sc.tc[i];
-    const V3<T> v0 = xyz<T>(A), e1 = xyz<T>(Bq), e2 = xyz<T>(C);
-    const T c0 = T(A.w), c1 = T(Bq.w), c2 = T(C.w);
-    const V3<T> b = start - v0;
-    const T detA = (nd.x * c0 - nd.y * c1) + nd.z * c2;
-    const T inv = rcp_(detA);
-    const T t = ((b.x * c0 - b.y * c1) + b.z * c2) * inv;
-    const T u = ((nd.x * (b.y * e2.z - b.z * e2.y) - nd.y * (b.x * e2.z - b.z * e2.x)) + nd.z * (b.x * e2.y - b.y * e2.x)) * inv;
-    const T v = ((nd.x * (e1.y * b.z - e1.z * b.y) - nd.y * (e1.x * b.z - e1.z * b.x)) + nd.z * (e1.x * b.y - e1.y * b.x)) * inv;
-    if (t < current_t && u >= T(0.0f) && v >= T(0.0f) && (u + v) <= T(1.0f) && t >= T(0.0f)) {
-      best = i;
-      best_u = u;
-      best_v = v;
-      current_t = t;
+// |d_k|^2 of the CH shadow directions (fast policy only)
+template <class T, int CH> struct ShadowRays {
+  V3<T> d[CH];
+  T dd[CH];
+  __device__ __forceinline__ void finish() {
+    if constexpr (!is_strict<T>::value) {
+#pragma unroll
+      for (int k = 0; k < CH; k++) dd[k] = d[k].x * d[k].x + d[k].y * d[k].y + d[k].z * d[k].z;
     }
   }
-  if (best >= 0) {
-    // (v0 + u*e1) + v*e2 of the winning triangle — same values as storing at acceptance time
-    const V3<T> v0 = xyz<T>(sc.ta[best]), e1 = xyz<T>(sc.tb[best]), e2 = xyz<T>(sc.tc[best]);
-    hit.id = best;
-    hit.point = (v0 + scale(best_u, e1)) + scale(best_v, e2);
-    hit.normal = xyz<T>(sc.tn[best]);
-    hit.color = sc.tcol[best];
+};
+
+// One (origin, triangle) pair of in_shadow (kernels.cl:246-276) against CH rays; ORs hits into occ.
+template <class T, int CH>
+__device__ __forceinline__ void shadow_pair(float4 A, float4 Bq, float4 C, V3<T> start, const ShadowRays<T, CH> &rays, T radius_sq,
+                                            unsigned &occ, unsigned alive = 0xffffffffu) {
+  const V3<T> v0 = xyz<T>(A), e1 = xyz<T>(Bq), e2 = xyz<T>(C);
+  const T c0 = T(A.w), c1 = T(Bq.w), c2 = T(C.w);
+  const V3<T> b = start - v0;
+  const T detA0 = (b.x * c0 - b.y * c1) + b.z * c2;
+  // cofactors of det[-d, b, e2] and det[-d, e1, b]: independent of the sample
+  const T U0 = b.y * e2.z - b.z * e2.y, U1 = b.x * e2.z - b.z * e2.x, U2 = b.x * e2.y - b.y * e2.x;
+  const T V0 = e1.y * b.z - e1.z * b.y, V1 = e1.x * b.z - e1.z * b.x, V2 = e1.x * b.y - e1.y * b.x;
+  if constexpr (is_strict<T>::value) {
+#pragma unroll
+    for (int k = 0; k < CH; k++) {
+      if (((occ | ~alive) >> k) & 1u) continue;
+      const V3<T> nd = -rays.d[k];
+      const T detA = (nd.x * c0 - nd.y * c1) + nd.z * c2;
+      const T inv = rcp_(detA);
+      const T t = detA0 * inv;
+      const V3<T> dv = scale(t, rays.d[k]);
+      const T dist = dv.x * dv.x + dv.y * dv.y + dv.z * dv.z;
+      if (t >= T(0.0f) && dist < radius_sq) {
+        const T u = ((nd.x * U0 - nd.y * U1) + nd.z * U2) * inv;
+        const T v = ((nd.x * V0 - nd.y * V1) + nd.z * V2) * inv;
+        if (u >= T(0.0f) && v >= T(0.0f) && (u + v) <= T(1.0f)) occ |= 1u << k;
+      }
+    }
+  } else {
+    const T num2 = detA0 * detA0;
+#pragma unroll
+    for (int k = 0; k < CH; k++) {
+      // den = det[-d, e1, e2];  t = detA0/den
+      const T den = -((rays.d[k].x * c0 - rays.d[k].y * c1) + rays.d[k].z * c2);
+      // t >= 0  and  t^2 |d|^2 < r^2, without dividing (den == 0 fails the second test)
+      const bool s1 = (detA0 * den >= 0.0f) && (num2 * rays.dd[k] < radius_sq * (den * den)) && ((alive >> k) & 1u);
+      if (s1) {
+        const T sg = (den < 0.0f) ? -1.0f : 1.0f;
+        const T D1 = -((rays.d[k].x * U0 - rays.d[k].y * U1) + rays.d[k].z * U2) * sg;  // u * |den|
+        const T D2 = -((rays.d[k].x * V0 - rays.d[k].y * V1) + rays.d[k].z * V2) * sg;  // v * |den|
+        if (D1 >= 0.0f && D2 >= 0.0f && (D1 + D2) <= den * sg) occ |= 1u << k;
+      }
+    }
   }
-  closest_spheres<T>(start, dir, current_t, hit);
 }
 
-// ---------------------------------------------------------------------------
-// Any hit for CH shadow rays sharing one origin: kernels.cl:243-311.
-// Returns a bit mask: bit k set = sample k is in shadow.
-// ---------------------------------------------------------------------------
+// Sphere part of in_shadow (kernels.cl:278-307)
 template <class T, int CH>
-__device__ __forceinline__ unsigned shadow_chunk(const SceneView &sc, V3<T> start, const V3<T> (&d)[CH], T radius_sq) {
-  unsigned occ = 0u;
-  constexpr unsigned FULL = (CH >= 32) ? 0xffffffffu : ((1u << CH) - 1u);
-  [[maybe_unused]] T dd[CH];  // |d_k|^2 (fast policy)
-  if constexpr (!is_strict<T>::value) {
-#pragma unroll
-    for (int k = 0; k < CH; k++) dd[k] = d[k].x * d[k].x + d[k].y * d[k].y + d[k].z * d[k].z;
-  }
-  for (int i = 0; i < sc.n_sh; i++) {
-    const float4 A = sc.sa[i], Bq = sc.sb[i], C = sc.sc[i];
-    const V3<T> v0 = xyz<T>(A), e1 = xyz<T>(Bq), e2 = xyz<T>(C);
-    const T c0 = T(A.w), c1 = T(Bq.w), c2 = T(C.w);
-    const V3<T> b = start - v0;
-    const T detA0 = (b.x * c0 - b.y * c1) + b.z * c2;
-    // cofactors of det[-d, b, e2] and det[-d, e1, b]: independent of the sample
-    const T U0 = b.y * e2.z - b.z * e2.y, U1 = b.x * e2.z - b.z * e2.x, U2 = b.x * e2.y - b.y * e2.x;
-    const T V0 = e1.y * b.z - e1.z * b.y, V1 = e1.x * b.z - e1.z * b.x, V2 = e1.x * b.y - e1.y * b.x;
-    if constexpr (is_strict<T>::value) {
-#pragma unroll
-      for (int k = 0; k < CH; k++) {
-        if ((occ >> k) & 1u) continue;
-        const V3<T> nd = -d[k];
-        const T detA = (nd.x * c0 - nd.y * c1) + nd.z * c2;
-        const T inv = rcp_(detA);
-        const T t = detA0 * inv;
-        const V3<T> dv = scale(t, d[k]);
-        const T dist = dv.x * dv.x + dv.y * dv.y + dv.z * dv.z;
-        if (t >= T(0.0f) && dist < radius_sq) {
-          const T u = ((nd.x * U0 - nd.y * U1) + nd.z * U2) * inv;
-          const T v = ((nd.x * V0 - nd.y * V1) + nd.z * V2) * inv;
-          if (u >= T(0.0f) && v >= T(0.0f) && (u + v) <= T(1.0f)) occ |= 1u << k;
-        }
-      }
-    } else {
-      const T num2 = detA0 * detA0;
-#pragma unroll
-      for (int k = 0; k < CH; k++) {
-        // den = det[-d, e1, e2];  t = detA0/den
-        const T den = -((d[k].x * c0 - d[k].y * c1) + d[k].z * c2);
-        // t >= 0  and  t^2 |d|^2 < r^2, without dividing (den == 0 fails the second test)
-        const bool s1 = (detA0 * den >= 0.0f) && (num2 * dd[k] < radius_sq * (den * den));
-        if (s1) {
-          const T sg = (den < 0.0f) ? -1.0f : 1.0f;
-          const T D1 = -((d[k].x * U0 - d[k].y * U1) + d[k].z * U2) * sg;  // u * |den|
-          const T D2 = -((d[k].x * V0 - d[k].y * V1) + d[k].z * V2) * sg;  // v * |den|
-          if (D1 >= 0.0f && D2 >= 0.0f && (D1 + D2) <= den * sg) occ |= 1u << k;
-        }
-      }
-    }
-    if (occ == FULL) return occ;
-  }
+__device__ __forceinline__ void shadow_spheres(V3<T> start, const ShadowRays<T, CH> &rays, T radius_sq, unsigned &occ) {
 #pragma unroll
   for (int i = 0; i < RT_SPHERES; i++) {
     if (c_sphere_color[i].w == -1.0f) continue;  // glass casts no shadow (kernels.cl:279)
@@ -185,8 +201,8 @@ __device__ __forceinline__ unsigned shadow_chunk(const SceneView &sc, V3<T> star
 #pragma unroll
     for (int k = 0; k < CH; k++) {
       if ((occ >> k) & 1u) continue;
-      const T a = dot(d[k], d[k]);
-      const T b = T(2.0f) * dot(d[k], L);
+      const T a = dot(rays.d[k], rays.d[k]);
+      const T b = T(2.0f) * dot(rays.d[k], L);
       const T disc = b * b - T(4.0f) * a * c;
       if (disc < T(0.0f)) continue;
       T x0, x1;
@@ -203,23 +219,63 @@ __device__ __forceinline__ unsigned shadow_chunk(const SceneView &sc, V3<T> star
       }
       const T x_min = cl_min(x0, x1);
       const T x_max = cl_max(x0, x1);
-      const V3<T> min_dir = scale(x_min, d[k]);
-      const V3<T> max_dir = scale(x_max, d[k]);
+      const V3<T> min_dir = scale(x_min, rays.d[k]);
+      const V3<T> max_dir = scale(x_max, rays.d[k]);
       const T min_dist = dot(min_dir, min_dir);
       const T max_dist = dot(max_dir, max_dir);
       if ((x_min >= T(0.0f) && min_dist < radius_sq) || (x_max >= T(0.0f) && max_dist < radius_sq)) occ |= 1u << k;
     }
   }
-  return occ;
+}
+
+// ---------------------------------------------------------------------------
+// Tracer: brute force over the shared-memory scene.
+//   closest(start, dir, hit)           kernels.cl:92-166 / :168-241
+//   shadow(start, rays, r, radius_sq)  kernels.cl:243-311 for CH rays sharing an origin -> occlusion mask
+// ---------------------------------------------------------------------------
+template <class T> struct BruteTracer {
+  SceneView sc;
+
+  __device__ __forceinline__ void closest(V3<T> start, V3<T> dir, HitRec<T> &hit) const {
+    ClosestState<T> cs;
+    cs.reset();
+    const V3<T> nd = -dir;
+    for (int i = 0; i < sc.n; i++) closest_tri_test<T, true>(sc.ta[i], sc.tb[i], sc.tc[i], start, nd, i, i, cs);
+    if (cs.id >= 0) {
+      hit.id = cs.id;
+      hit.point = hit_point<T>(sc.ta[cs.id], sc.tb[cs.id], sc.tc[cs.id], cs.u, cs.v);
+      hit.normal = xyz<T>(sc.tn[cs.id]);
+      hit.color = sc.tcol[cs.id];
+    }
+    closest_spheres<T>(start, dir, cs.t, hit);
+  }
+
+  template <int CH>
+  __device__ __forceinline__ unsigned shadow(V3<T> start, const ShadowRays<T, CH> &rays, V3<T> r, T radius_sq) const {
+    constexpr unsigned FULL = (CH >= 32) ? 0xffffffffu : ((1u << CH) - 1u);
+    unsigned occ = 0u;
+    for (int i = 0; i < sc.n_sh; i++) {
+      shadow_pair<T, CH>(sc.sa[i], sc.sb[i], sc.sc[i], start, rays, radius_sq, occ);
+      if (occ == FULL) return occ;
+    }
+    shadow_spheres<T, CH>(start, rays, radius_sq, occ);
+    return occ;
+  }
+};
+
+// Compatibility wrapper used by the fast kernel for its bounce rays.
+template <class T> __device__ __forceinline__ void closest_hit(const SceneView &sc, V3<T> start, V3<T> dir, HitRec<T> &hit) {
+  BruteTracer<T> tr;
+  tr.sc = sc;
+  tr.closest(start, dir, hit);
 }
 
 // ---------------------------------------------------------------------------
 // direct_light: kernels.cl:313-340.  The jitter sequence depends on the pixel
 // id only (same S jitters for every AA sample and bounce of a pixel).
 // ---------------------------------------------------------------------------
-template <class T, int CH>
-__device__ __forceinline__ V3<T> direct_light(const SceneView &sc, V3<T> point, V3<T> normal, V3<T> light_pos, int S,
-                                              int global_id) {
+template <class T, int CH, class Tracer>
+__device__ __forceinline__ V3<T> direct_light(const Tracer &tr, V3<T> point, V3<T> normal, V3<T> light_pos, int S, int global_id) {
   // (uint3)(global_id, global_id*91.0f, global_id*19.0f) then one xorshift (kernels.cl:319)
   uint32_t rx = xorshift32((uint32_t)global_id);
   uint32_t ry = xorshift32(__float2uint_rz(__fmul_rn(__int2float_rn(global_id), 91.0f)));
@@ -232,15 +288,16 @@ __device__ __forceinline__ V3<T> direct_light(const SceneView &sc, V3<T> point, 
   T total = T(0.0f);
   [[maybe_unused]] int lit = 0;
   for (int s0 = 0; s0 < S; s0 += CH) {
-    V3<T> d[CH];
+    ShadowRays<T, CH> rays;
 #pragma unroll
     for (int k = 0; k < CH; k++) {
       rx = xorshift32(rx);
       ry = xorshift32(ry);
       rz = xorshift32(rz);
-      d[k] = dir + V3<T>(crush1<T>(rx, RT_LIGHT_SPREAD), crush1<T>(ry, RT_LIGHT_SPREAD), crush1<T>(rz, RT_LIGHT_SPREAD));
+      rays.d[k] = dir + V3<T>(crush1<T>(rx, RT_LIGHT_SPREAD), crush1<T>(ry, RT_LIGHT_SPREAD), crush1<T>(rz, RT_LIGHT_SPREAD));
     }
-    unsigned occ = shadow_chunk<T, CH>(sc, start, d, radius_sq);
+    rays.finish();
+    unsigned occ = tr.template shadow<CH>(start, rays, dir, radius_sq);
     if (s0 + CH > S) occ |= ~0u << (S - s0);  // ragged last chunk: ignore the padding samples
     if constexpr (is_strict<T>::value) {
 #pragma unroll
@@ -292,28 +349,6 @@ __device__ __forceinline__ void refract_ray(V3<T> dir, V3<T> normal, V3<T> point
   o_dir = normalize(r);
 }
 
-// secondary_light: kernels.cl:342-365
-template <class T, int CH>
-__device__ __forceinline__ V3<T> secondary_light(const SceneView &sc, V3<T> dir, HitRec<T> hit, V3<T> light_pos, int S, int B,
-                                                 int global_id) {
-  float medium = RT_AIR;
-  for (int b = 0; b < B && hit.color.w <= 0.0f; b++) {
-    V3<T> start, ndir;
-    if (hit.color.w == 0.0f) reflect_ray<T>(dir, hit.normal, hit.point, start, ndir, medium);
-    else refract_ray<T>(dir, hit.normal, hit.point, medium, start, ndir, medium);
-    dir = ndir;
-    hit.id = -1;
-    hit.color.w = 1.0f;
-    closest_hit<T>(sc, start, dir, hit);
-    if (hit.id != -1 && hit.color.w > 0.0f) {
-      const V3<T> dl = direct_light<T, CH>(sc, hit.point, hit.normal, light_pos, S, global_id);
-      const V3<T> light(T(RT_INDIRECT) + dl.x, T(RT_INDIRECT) + dl.y, T(RT_INDIRECT) + dl.z);
-      return scale(T(0.9f), light) * xyz<T>(hit.color);
-    }
-  }
-  return V3<T>(T(0.0f), T(0.0f), T(0.0f));
-}
-
 // kernels.cl:37-40
 template <class T> __device__ __forceinline__ uint32_t pack_argb(V3<T> c) {
   const uint32_t r = __float2uint_rz(raw(cl_min(cl_max(T(255.0f) * c.x, T(0.f)), T(255.f))));
@@ -322,9 +357,11 @@ template <class T> __device__ __forceinline__ uint32_t pack_argb(V3<T> c) {
   return (255u << 24) + (r << 16) + (g << 8) + b;
 }
 
-// One pixel of `draw` (kernels.cl:368-428).
-template <class T, int CH>
-__device__ __forceinline__ uint32_t shade_pixel(const SceneView &sc, const FrameParams &p, int x, int y) {
+// One pixel of `draw` (kernels.cl:368-428).  The direct light of a diffuse hit and the tail of
+// secondary_light (kernels.cl:342-365) share one call site: per ray, loop { miss -> black; diffuse ->
+// shade (x0.9 after a bounce) and stop; mirror/glass -> bounce, up to B times }.
+template <class T, int CH, class Tracer>
+__device__ __forceinline__ uint32_t shade_pixel(const Tracer &tr, const FrameParams &p, int x, int y) {
   const T SW = T(__int2float_rn(p.W)), SH = T(__int2float_rn(p.H));
   const int A = p.A;
   const T fA = T(__int2float_rn(A));
@@ -334,21 +371,37 @@ __device__ __forceinline__ uint32_t shade_pixel(const SceneView &sc, const Frame
   const V3<T> r0(T(p.rot[0]), T(p.rot[1]), T(p.rot[2])), r1(T(p.rot[3]), T(p.rot[4]), T(p.rot[5])), r2(T(p.rot[6]), T(p.rot[7]), T(p.rot[8]));
   const V3<T> cam(T(p.cam[0]), T(p.cam[1]), T(p.cam[2])), light(T(p.light[0]), T(p.light[1]), T(p.light[2]));
   V3<T> total(T(0.0f), T(0.0f), T(0.0f));
+#pragma unroll 1
   for (int dy = 0; dy < A; dy++) {
+#pragma unroll 1
     for (int dx = 0; dx < A; dx++) {
       const V3<T> d0 = base + V3<T>(T(__int2float_rn(dx)), T(__int2float_rn(dy)), T(0.0f));
-      const V3<T> dir = normalize(V3<T>(dot(r0, d0), dot(r1, d0), dot(r2, d0)));
+      V3<T> dir = normalize(V3<T>(dot(r0, d0), dot(r1, d0), dot(r2, d0)));
       HitRec<T> hit;
       hit.id = -1;
       hit.color = make_float4(0.0f, 0.0f, 0.0f, 1.0f);
-      closest_hit<T>(sc, cam, dir, hit);
-      if (hit.id != -1) {
-        if (hit.color.w <= 0.0f) {
-          total = total + secondary_light<T, CH>(sc, dir, hit, light, p.S, p.B, global_id);
-        } else {
-          const V3<T> fl = direct_light<T, CH>(sc, hit.point, hit.normal, light, p.S, global_id);
-          total = total + xyz<T>(hit.color) * V3<T>(T(RT_INDIRECT) + fl.x, T(RT_INDIRECT) + fl.y, T(RT_INDIRECT) + fl.z);
+      tr.closest(cam, dir, hit);
+      float medium = RT_AIR;
+      bool bounced = false;
+      int bounce = 0;
+      while (hit.id != -1) {
+        if (hit.color.w > 0.0f) {
+          const V3<T> dl = direct_light<T, CH, Tracer>(tr, hit.point, hit.normal, light, p.S, global_id);
+          const V3<T> lightv(T(RT_INDIRECT) + dl.x, T(RT_INDIRECT) + dl.y, T(RT_INDIRECT) + dl.z);
+          // primary: colour*(indirect + direct) (kernels.cl:422); after a bounce: 0.9*light*colour (:355)
+          total = total + (bounced ? scale(T(0.9f), lightv) * xyz<T>(hit.color) : xyz<T>(hit.color) * lightv);
+          break;
         }
+        if (bounce >= p.B) break;
+        bounce++;
+        V3<T> start, ndir;
+        if (hit.color.w == 0.0f) reflect_ray<T>(dir, hit.normal, hit.point, start, ndir, medium);
+        else refract_ray<T>(dir, hit.normal, hit.point, medium, start, ndir, medium);
+        dir = ndir;
+        hit.id = -1;
+        hit.color.w = 1.0f;
+        tr.closest(start, dir, hit);
+        bounced = true;
       }
     }
   }

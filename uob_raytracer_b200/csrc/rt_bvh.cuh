@@ -1,0 +1,202 @@
+// rt_bvh.cuh — BVH tracer for large meshes (Loader.cpp scenes: ~1 M triangles in the box).
+//
+// The reference has no acceleration structure: every ray tests every triangle
+// (kernels.cl:100, :174, :246), which is ~10^14 tests per 1080p frame at 1 M triangles.
+// Here a GPU-built LBVH (rt_bvh.cu) only PRUNES: a leaf hands its triangles to exactly the
+// per-triangle tests of the brute-force path (rt_brute.cuh), boxes are padded well beyond
+// rounding error, and the reference's tie rule (lowest upload index wins an equal t) is applied
+// explicitly, so a BVH frame equals the brute-force frame — bit for bit under RT_FLAG_STRICT_IEEE.
+//
+// Layout (all in HBM, float4 = one 16-byte load):
+//   tri_a/b/c[s]   (v0,c0) (e1,c1) (e2,c2) of the triangle at sorted slot s   (same as SceneView)
+//   tri_n/col[s]   normal, colour+material;  tri_id[s] = upload index
+//   slots [0, n_bvh) are in Morton order and covered by the tree; slots [n_bvh, n) hold the few
+//   "big" triangles (room walls) that would bloat the boxes — they are tested linearly.
+//   node j = 4 float4: child0 box min.xyz max.x | child0 max.yz child1 min.xy | child1 min.z max.xyz |
+//            (ref0, ref1, -, -) as ints.  ref >= 0: internal node; ref < 0: leaf, ~ref = first<<3 | (count-1).
+//
+// Shadow rays: the S jittered rays of a shading point share their origin and nearly their
+// direction, so they traverse the tree as ONE packet with a per-node mask of live rays: node
+// fetches are shared, a leaf runs the same (origin, triangle) x CH-rays test as the brute-force
+// path on the rays that reach it.
+#pragma once
+#include "rt_brute.cuh"
+
+namespace rt {
+
+constexpr int kBvhLeafMax = 4;       // triangles per leaf (<= 8 by the ref encoding)
+constexpr int kBvhStack = 64;
+constexpr float kBvhJitterMax = 0.0445f;  // same inflated bound as the fast brute-force path
+
+struct BvhView {
+  const float4 *tri_a, *tri_b, *tri_c, *tri_n, *tri_col;
+  const int *tri_id;
+  const float4 *nodes;
+  int n, n_bvh;      // all triangles / those covered by the tree
+  int root;          // root reference (may be a leaf)
+  int all_casters;   // no triangle has material -1
+};
+
+__device__ __forceinline__ float safe_rcp_dir(float d) {
+  const float a = fabsf(d) < 1e-20f ? copysignf(1e-20f, d) : d;
+  return 1.0f / a;
+}
+
+// Slab test of the ray o + t*d, t in [0, tmax], against [lo, hi]; returns entry distance or -1.
+__device__ __forceinline__ float box_entry(float lox, float loy, float loz, float hix, float hiy, float hiz, float ox, float oy, float oz,
+                                           float ix, float iy, float iz, float tmax) {
+  const float tx0 = (lox - ox) * ix, tx1 = (hix - ox) * ix;
+  const float ty0 = (loy - oy) * iy, ty1 = (hiy - oy) * iy;
+  const float tz0 = (loz - oz) * iz, tz1 = (hiz - oz) * iz;
+  const float tn = fmaxf(fmaxf(fminf(tx0, tx1), fminf(ty0, ty1)), fmaxf(fminf(tz0, tz1), 0.0f));
+  const float tf = fminf(fminf(fmaxf(tx0, tx1), fmaxf(ty0, ty1)), fminf(fmaxf(tz0, tz1), tmax));
+  return (tn <= tf) ? tn : -1.0f;
+}
+
+template <class T> struct BvhTracer {
+  BvhView bv;
+
+  // kernels.cl:92-166 / :168-241
+  __device__ void closest(V3<T> start, V3<T> dir, HitRec<T> &hit) const {
+    ClosestState<T> cs;
+    cs.reset();
+    const V3<T> nd = -dir;
+    // the big triangles, linearly
+    for (int s = bv.n_bvh; s < bv.n; s++)
+      closest_tri_test<T, false>(bv.tri_a[s], bv.tri_b[s], bv.tri_c[s], start, nd, bv.tri_id[s], s, cs);
+    if (bv.n_bvh > 0) {
+      const float ox = raw(start.x), oy = raw(start.y), oz = raw(start.z);
+      const float ix = safe_rcp_dir(raw(dir.x)), iy = safe_rcp_dir(raw(dir.y)), iz = safe_rcp_dir(raw(dir.z));
+      int stack[kBvhStack];
+      int sp = 0;
+      int ref = bv.root;
+      for (;;) {
+        if (ref >= 0) {
+          const float4 *nd4 = bv.nodes + 4 * (size_t)ref;
+          const float4 n0 = __ldg(nd4), n1 = __ldg(nd4 + 1), n2 = __ldg(nd4 + 2), n3 = __ldg(nd4 + 3);
+          const float tmax = raw(cs.t);
+          const float e0 = box_entry(n0.x, n0.y, n0.z, n0.w, n1.x, n1.y, ox, oy, oz, ix, iy, iz, tmax);
+          const float e1 = box_entry(n1.z, n1.w, n2.x, n2.y, n2.z, n2.w, ox, oy, oz, ix, iy, iz, tmax);
+          const int r0 = __float_as_int(n3.x), r1 = __float_as_int(n3.y);
+          if (e0 >= 0.0f && e1 >= 0.0f) {
+            const bool first0 = e0 <= e1;
+            if (sp < kBvhStack) stack[sp++] = first0 ? r1 : r0;
+            ref = first0 ? r0 : r1;
+            continue;
+          }
+          if (e0 >= 0.0f) {
+            ref = r0;
+            continue;
+          }
+          if (e1 >= 0.0f) {
+            ref = r1;
+            continue;
+          }
+        } else {
+          const int first = (~ref) >> 3, cnt = ((~ref) & 7) + 1;
+          for (int k = 0; k < cnt; k++) {
+            const int s = first + k;
+            closest_tri_test<T, false>(__ldg(bv.tri_a + s), __ldg(bv.tri_b + s), __ldg(bv.tri_c + s), start, nd, __ldg(bv.tri_id + s), s, cs);
+          }
+        }
+        if (sp == 0) break;
+        ref = stack[--sp];
+      }
+    }
+    if (cs.id >= 0) {
+      const int s = cs.slot;
+      hit.id = cs.id;
+      hit.point = hit_point<T>(bv.tri_a[s], bv.tri_b[s], bv.tri_c[s], cs.u, cs.v);
+      hit.normal = xyz<T>(bv.tri_n[s]);
+      hit.color = bv.tri_col[s];
+    }
+    closest_spheres<T>(start, dir, cs.t, hit);
+  }
+
+  __device__ __forceinline__ bool casts_shadow(int s) const { return bv.all_casters || __ldg(&bv.tri_col[s].w) != -1.0f; }
+
+  // kernels.cl:243-311 for CH rays start + t (r + j_k): occlusion mask
+  template <int CH>
+  __device__ unsigned shadow(V3<T> start, const ShadowRays<T, CH> &rays, V3<T> r, T radius_sq) const {
+    constexpr unsigned FULL = (CH >= 32) ? 0xffffffffu : ((1u << CH) - 1u);
+    unsigned occ = 0u;
+    for (int s = bv.n_bvh; s < bv.n; s++) {
+      if (!casts_shadow(s)) continue;
+      shadow_pair<T, CH>(bv.tri_a[s], bv.tri_b[s], bv.tri_c[s], start, rays, radius_sq, occ);
+      if (occ == FULL) return occ;
+    }
+    if (bv.n_bvh > 0) {
+      // Packet traversal: the CH rays share every node fetch; each node is tested against every ray
+      // that is still alive for it (slab test over 0 <= t <= |r|/|d_k|, the reference's distance
+      // limit), and a leaf tests only those rays.  A node is dropped when no live, unoccluded ray
+      // touches its (padded) box.
+      const float ox = raw(start.x), oy = raw(start.y), oz = raw(start.z);
+      const float R = sqrtf(raw(radius_sq));
+      float ix[CH], iy[CH], iz[CH], tm[CH];
+#pragma unroll
+      for (int k = 0; k < CH; k++) {
+        const float dx = raw(rays.d[k].x), dy = raw(rays.d[k].y), dz = raw(rays.d[k].z);
+        ix[k] = safe_rcp_dir(dx);
+        iy[k] = safe_rcp_dir(dy);
+        iz[k] = safe_rcp_dir(dz);
+        tm[k] = 1.0001f * R * rsqrtf(dx * dx + dy * dy + dz * dz);
+      }
+      int stack[kBvhStack];
+      unsigned mstack[kBvhStack];
+      int sp = 0;
+      int ref = bv.root;
+      unsigned alive = FULL;
+      for (;;) {
+        alive &= ~occ;
+        if (alive) {
+          if (ref >= 0) {
+            const float4 *nd4 = bv.nodes + 4 * (size_t)ref;
+            const float4 n0 = __ldg(nd4), n1 = __ldg(nd4 + 1), n2 = __ldg(nd4 + 2), n3 = __ldg(nd4 + 3);
+            unsigned m0 = 0u, m1 = 0u;
+#pragma unroll
+            for (int k = 0; k < CH; k++) {
+              if (!((alive >> k) & 1u)) continue;
+              if (box_entry(n0.x, n0.y, n0.z, n0.w, n1.x, n1.y, ox, oy, oz, ix[k], iy[k], iz[k], tm[k]) >= 0.0f) m0 |= 1u << k;
+              if (box_entry(n1.z, n1.w, n2.x, n2.y, n2.z, n2.w, ox, oy, oz, ix[k], iy[k], iz[k], tm[k]) >= 0.0f) m1 |= 1u << k;
+            }
+            const int r0 = __float_as_int(n3.x), r1 = __float_as_int(n3.y);
+            if (m0 && m1) {
+              if (sp < kBvhStack) {
+                stack[sp] = r1;
+                mstack[sp++] = m1;
+              }
+              ref = r0;
+              alive = m0;
+              continue;
+            }
+            if (m0) {
+              ref = r0;
+              alive = m0;
+              continue;
+            }
+            if (m1) {
+              ref = r1;
+              alive = m1;
+              continue;
+            }
+          } else {
+            const int first = (~ref) >> 3, cnt = ((~ref) & 7) + 1;
+            for (int k = 0; k < cnt; k++) {
+              const int s = first + k;
+              if (!casts_shadow(s)) continue;
+              shadow_pair<T, CH>(__ldg(bv.tri_a + s), __ldg(bv.tri_b + s), __ldg(bv.tri_c + s), start, rays, radius_sq, occ, alive);
+            }
+            if (occ == FULL) return occ;
+          }
+        }
+        if (sp == 0) break;
+        ref = stack[--sp];
+        alive = mstack[sp];
+      }
+    }
+    shadow_spheres<T, CH>(start, rays, radius_sq, occ);
+    return occ;
+  }
+};
+
+}  // namespace rt

@@ -15,11 +15,12 @@ template <class T, int CH>
 __global__ void __launch_bounds__(kThreads) draw_brute_kernel(const __grid_constant__ FrameParams p, const float4 *__restrict__ scene,
                                                               int n, int n_sh) {
   extern __shared__ float4 smem[];
-  const SceneView sc = stage_scene(smem, scene, n, n_sh);
+  BruteTracer<T> tr;
+  tr.sc = stage_scene(smem, scene, n, n_sh);
   __syncthreads();
   int x, y, tx, ty;
   if (!pixel_of_thread(p, x, y, tx, ty)) return;
-  p.out[(size_t)y * p.W + x] = shade_pixel<T, CH>(sc, p, x, y);
+  p.out[(size_t)y * p.W + x] = shade_pixel<T, CH, BruteTracer<T>>(tr, p, x, y);
 }
 
 // strict kernel: 5n + 3n_sh float4; fast kernel: 5n (generic) + 3n (primary constants) + 4n_sh

@@ -26,6 +26,8 @@ struct rt_ctx {
   int n = 0, n_sh = 0;
   bool have_scene = false;
   bool use_bvh = false;
+  void *bvh_view = nullptr;         // rt::BvhView (rt_bvh.cu)
+  std::vector<void *> bvh_allocs;   // device allocations owned by the BVH
   int sm_count = 0;
   uint64_t launches = 0;
   size_t launch_extra_smem = 0;  // set by a launcher that needs shared memory beyond the scene
@@ -38,6 +40,10 @@ namespace rt {
 cudaError_t launch_draw_brute(rt_ctx *ctx, const FrameParams &fp, cudaStream_t stream);
 size_t brute_smem_bytes(int n, int n_sh);
 size_t brute_smem_limit();
+// rt_bvh.cu
+cudaError_t bvh_build(rt_ctx *ctx, const float *verts, const float *normals, const float *colors, int n);
+void bvh_free(rt_ctx *ctx);
+cudaError_t launch_draw_bvh(rt_ctx *ctx, const FrameParams &fp, cudaStream_t stream);
 // rt_draw_fast.cu, one translation unit per shadow chunk size
 cudaError_t launch_fast_ch1(rt_ctx *ctx, const FrameParams &fp, cudaStream_t stream);
 cudaError_t launch_fast_ch2(rt_ctx *ctx, const FrameParams &fp, cudaStream_t stream);
