@@ -82,7 +82,21 @@ def build(force: bool = False, verbose: bool = False) -> str:
     objs = [os.path.join(PKG, "build", j[2]) for j in jobs]
     cmd = [_nvcc(), "-Wno-deprecated-gpu-targets", "-shared", "-o", LIB, *objs, "-lcudart"]
     subprocess.check_call(cmd)
+    build_skeleton()
     return LIB
+
+
+HOST_EXE = os.path.join(PKG, "skeleton_b200")
+
+
+def build_skeleton() -> str:
+    """The reference's host loop on the new path (csrc/host/skeleton_b200.cpp), linked against both libraries."""
+    src = os.path.join(CSRC, "host", "skeleton_b200.cpp")
+    if os.environ.get("UOB_RT_LIB"):
+        return HOST_EXE  # kernel-variant experiment builds do not relink the host program
+    subprocess.check_call(["g++", "-std=c++17", "-O2", "-Wall", src, "-o", HOST_EXE, "-L", PKG, "-luob_rt", "-luob_host",
+                           "-Wl,-rpath,$ORIGIN"])
+    return HOST_EXE
 
 
 if __name__ == "__main__":
