@@ -48,6 +48,16 @@ def load_counts(workload: str) -> dict:
         return json.load(f)[workload]
 
 
+def load_traffic(workload: str):
+    """DRAM bytes per launch of the dominant kernel from the committed ncu capture (profiles/traffic.json)."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+            t = json.load(f)[workload]
+        return t["dram_bytes_read"] + t["dram_bytes_write"]
+    except Exception:
+        return None
+
+
 def algorithmic_flops(c: dict) -> float:
     """minimal-operation form of the reference's brute-force algorithm, FMA = 2."""
     return 37.0 * c["closest_tri_tests"] + 17.0 * c["shadow_stage1_tests"] + 22.0 * c["shadow_stage2_tests"] + \
@@ -357,7 +367,7 @@ def run_ours(args, cfg) -> int:
                          "peak_source": "FFMA microbenchmark in this run (rt_measure_fp32_peak); MEASURED_PEAKS.json has no FP32 entry",
                          "peak_nominal": round(nominal, 1), "frac_of_nominal": round(achieved / nominal, 4),
                          "algorithmic_gflop_per_launch": round(flops / 1e9, 3),
-                         "traffic": None},
+                         "traffic": load_traffic(cfg.name)},
         }
         # CPU baseline on this box's host cores (N = 1 only)
         if world == 1 and not args.no_cpu_baseline:

@@ -87,7 +87,9 @@ int rt_upload_scene(rt_ctx *ctx, const float *verts_xyzw, const float *normals_x
  * the 16 bytes the reference passes as float3 (w ignored, :162-165).
  * host_argb receives rows [row0,row0+rows) only: rows*width uint32 ARGB8888
  * (kernels.cl:37-40), i.e. the whole frame for an untiled context.  The frame
- * is valid on return. */
+ * is valid on return.  Internally the tile is rendered in four row bands whose
+ * read-back overlaps the rendering of the next band; pass pinned memory
+ * (cudaHostAlloc / cudaHostRegister) for the overlap and full copy speed. */
 int rt_render(rt_ctx *ctx, const float rot12[12], const float cam[4], const float light[4],
               float focal_length, uint32_t *host_argb);
 

@@ -17,8 +17,21 @@ def stats(a, b):
     return dict(neq=int((a != b).sum()), gt1=int((d > 1).sum()), maxdiff=int(d.max()), frac_gt1=float((d > 1).mean()))
 
 cases = [("head", 1024, 1024, 2, 10, 10), ("cfg1", 1024, 1024, 1, 1, 0), ("cfg2", 1920, 1080, 2, 8, 10), ("cfg3q", 960, 540, 4, 10, 4)]
+big = {"cfg3": (3840, 2160, 4, 10, 4), "cfg5": (7680, 4320, 2, 10, 10)}
 if len(sys.argv) > 1:
     cases = [c for c in cases if c[0] in sys.argv[1:]]
+import json as _json
+counts = _json.load(open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden", "ray_counts.json")))
+for name in [a for a in sys.argv[1:] if a in big]:
+    W, H, A, S, B = big[name]
+    f = 1100.0 * A * H / 1024
+    with u.Renderer(W, H, A, S, B) as r:
+        r.upload_scene(scene)
+        ms = []
+        for _ in range(5):
+            r.render_device(rot, cam4, light4, f)
+            ms.append(r.last_kernel_ms)
+    print(name, "fast kernel ms", round(min(ms), 3), "Mrays/s", round(counts[name]["rays"] / min(ms) / 1e3, 1), flush=True)
 for name, W, H, A, S, B in cases:
     f = 1100.0 * A * H / 1024
     t = time.time()

@@ -15,7 +15,7 @@ if [ "${1:-}" = "ncu" ]; then
       python bench.py --steps 3 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_launches.log 2>&1
   echo "ncu launches rc=$?"
   python bench.py --steps 3 --warmup 3 --no-cpu-baseline > gpurun_out/plain2.log 2>&1 &&
-  ncu --set full --clock-control none --import-source on -k regex:draw_brute -s 3 -c 2 -f -o gpurun_out/prof \
+  ncu --set full --clock-control none --import-source on -k regex:draw_ -s 3 -c 2 -f -o gpurun_out/prof \
       python bench.py --steps 3 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_full.log 2>&1
   echo "ncu full rc=$?"
 fi

@@ -47,6 +47,11 @@ static int free_ctx(rt_ctx *ctx) {
   if (ctx->d_frame) cudaFree(ctx->d_frame);
   if (ctx->d_scene) cudaFree(ctx->d_scene);
   rt::bvh_free(ctx);
+  for (int b = 0; b < rt_ctx::kBands; b++) {
+    if (ctx->band_stream[b]) cudaStreamDestroy(ctx->band_stream[b]);
+    if (ctx->band_done[b]) cudaEventDestroy(ctx->band_done[b]);
+  }
+  if (ctx->band_start) cudaEventDestroy(ctx->band_start);
   if (ctx->ev0) cudaEventDestroy(ctx->ev0);
   if (ctx->ev1) cudaEventDestroy(ctx->ev1);
   if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
@@ -108,6 +113,11 @@ rt_ctx *rt_create(const rt_config *cfg) {
   ctx->stream = ctx->own_stream;
   if ((e = cudaEventCreate(&ctx->ev0)) != cudaSuccess) return fail("creating event", e);
   if ((e = cudaEventCreate(&ctx->ev1)) != cudaSuccess) return fail("creating event", e);
+  for (int b = 0; b < rt_ctx::kBands; b++) {
+    if ((e = cudaStreamCreateWithFlags(&ctx->band_stream[b], cudaStreamNonBlocking)) != cudaSuccess) return fail("creating stream", e);
+    if ((e = cudaEventCreateWithFlags(&ctx->band_done[b], cudaEventDisableTiming)) != cudaSuccess) return fail("creating event", e);
+  }
+  if ((e = cudaEventCreateWithFlags(&ctx->band_start, cudaEventDisableTiming)) != cudaSuccess) return fail("creating event", e);
   if ((e = cudaMalloc(&ctx->d_frame, sizeof(uint32_t) * (size_t)cfg->width * cfg->height)) != cudaSuccess)
     return fail("creating screen buffer", e);
   if ((e = cudaMemsetAsync(ctx->d_frame, 0, sizeof(uint32_t) * (size_t)cfg->width * cfg->height, ctx->stream)) != cudaSuccess)
@@ -196,7 +206,7 @@ int rt_upload_scene(rt_ctx *ctx, const float *verts, const float *normals, const
 }
 
 static int render_impl(rt_ctx *ctx, const float rot12[12], const float cam[4], const float light[4], float focal,
-                       uint32_t *dev_argb, cudaStream_t stream) {
+                       uint32_t *dev_argb, cudaStream_t stream, int band_row0 = -1, int band_rows = 0) {
   if (!ctx) return RT_ERR_INVALID;
   if (!ctx->have_scene) {
     ctx->err = "rt_render: no scene uploaded";
@@ -210,8 +220,8 @@ static int render_impl(rt_ctx *ctx, const float rot12[12], const float cam[4], c
   rt::FrameParams fp;
   fp.W = ctx->cfg.width;
   fp.H = ctx->cfg.height;
-  fp.row0 = ctx->row0;
-  fp.rows = ctx->rows;
+  fp.row0 = band_row0 >= 0 ? band_row0 : ctx->row0;
+  fp.rows = band_row0 >= 0 ? band_rows : ctx->rows;
   fp.A = ctx->cfg.aa;
   fp.S = ctx->cfg.shadow_samples;
   fp.B = ctx->cfg.max_bounces;
@@ -223,10 +233,13 @@ static int render_impl(rt_ctx *ctx, const float rot12[12], const float cam[4], c
     fp.light[c] = light[c];
   }
   fp.out = dev_argb ? dev_argb : ctx->d_frame;
-  RT_CUDA(ctx, cudaEventRecord(ctx->ev0, stream), "recording start event");
+  const bool whole = band_row0 < 0;
+  if (whole) RT_CUDA(ctx, cudaEventRecord(ctx->ev0, stream), "recording start event");
   RT_CUDA(ctx, ctx->use_bvh ? rt::launch_draw_bvh(ctx, fp, stream) : rt::launch_draw_brute(ctx, fp, stream), "enqueueing draw kernel");
-  RT_CUDA(ctx, cudaEventRecord(ctx->ev1, stream), "recording stop event");
-  ctx->timed = true;
+  if (whole) {
+    RT_CUDA(ctx, cudaEventRecord(ctx->ev1, stream), "recording stop event");
+    ctx->timed = true;
+  }
   return RT_OK;
 }
 
@@ -242,11 +255,38 @@ int rt_render(rt_ctx *ctx, const float rot12[12], const float cam[4], const floa
     ctx->err = "rt_render: host_argb is NULL";
     return RT_ERR_INVALID;
   }
-  int rc = render_impl(ctx, rot12, cam, light, focal, nullptr, ctx->stream);
-  if (rc != RT_OK) return rc;
-  const size_t off = (size_t)ctx->row0 * ctx->cfg.width, cnt = (size_t)ctx->rows * ctx->cfg.width;
-  RT_CUDA(ctx, cudaMemcpyAsync(host_argb, ctx->d_frame + off, sizeof(uint32_t) * cnt, cudaMemcpyDeviceToHost, ctx->stream),
-          "reading screen buffer data");
+  const int W = ctx->cfg.width;
+  // Band height: a multiple of the block height, about a quarter of the tile.  Small tiles and
+  // block-interleaved contexts (whose frame is completed by other GPUs) render in one piece.
+  int band_rows = ((ctx->rows + rt_ctx::kBands - 1) / rt_ctx::kBands + 15) / 16 * 16;
+  if (ctx->rows < 256 || ctx->cfg.block_stride > 1) band_rows = ctx->rows;
+  if (band_rows >= ctx->rows) {
+    int rc = render_impl(ctx, rot12, cam, light, focal, nullptr, ctx->stream);
+    if (rc != RT_OK) return rc;
+    const size_t off = (size_t)ctx->row0 * W, cnt = (size_t)ctx->rows * W;
+    RT_CUDA(ctx, cudaMemcpyAsync(host_argb, ctx->d_frame + off, sizeof(uint32_t) * cnt, cudaMemcpyDeviceToHost, ctx->stream),
+            "reading screen buffer data");
+    RT_CUDA(ctx, cudaStreamSynchronize(ctx->stream), "reading screen buffer data");
+    return RT_OK;
+  }
+  RT_CUDA(ctx, cudaSetDevice(ctx->cfg.device), "selecting device");
+  RT_CUDA(ctx, cudaEventRecord(ctx->ev0, ctx->stream), "recording start event");
+  RT_CUDA(ctx, cudaEventRecord(ctx->band_start, ctx->stream), "recording start event");
+  int nb = 0;
+  for (int r = 0; r < ctx->rows; r += band_rows, nb++) {
+    cudaStream_t bs = ctx->band_stream[nb];
+    const int rows = (r + band_rows <= ctx->rows) ? band_rows : ctx->rows - r;
+    RT_CUDA(ctx, cudaStreamWaitEvent(bs, ctx->band_start, 0), "ordering a band after the stream");
+    int rc = render_impl(ctx, rot12, cam, light, focal, nullptr, bs, ctx->row0 + r, rows);
+    if (rc != RT_OK) return rc;
+    const size_t off = (size_t)(ctx->row0 + r) * W;
+    RT_CUDA(ctx, cudaMemcpyAsync(host_argb + (size_t)r * W, ctx->d_frame + off, sizeof(uint32_t) * (size_t)rows * W, cudaMemcpyDeviceToHost, bs),
+            "reading screen buffer data");
+    RT_CUDA(ctx, cudaEventRecord(ctx->band_done[nb], bs), "recording band completion");
+  }
+  for (int b = 0; b < nb; b++) RT_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->band_done[b], 0), "joining the bands");
+  RT_CUDA(ctx, cudaEventRecord(ctx->ev1, ctx->stream), "recording stop event");
+  ctx->timed = true;
   RT_CUDA(ctx, cudaStreamSynchronize(ctx->stream), "reading screen buffer data");
   return RT_OK;
 }

@@ -18,6 +18,12 @@ struct rt_ctx {
   cudaStream_t stream = nullptr;      // the stream in use
   cudaStream_t own_stream = nullptr;  // created by rt_create
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  // rt_render overlaps the read-back with the kernel: the tile is rendered in kBands row bands on
+  // their own streams and each band is copied to the host as soon as it is done
+  static constexpr int kBands = 4;
+  cudaStream_t band_stream[kBands] = {};
+  cudaEvent_t band_done[kBands] = {};
+  cudaEvent_t band_start = nullptr;
   bool timed = false;
   uint32_t *d_frame = nullptr;  // whole frame, W*H
   // Brute-force scene: one float4 buffer, [ta|tb|tc|tn|tcol] x n, [sa|sb|sc] x n_sh (generic kernel),
