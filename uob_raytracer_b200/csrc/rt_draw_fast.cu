@@ -16,17 +16,20 @@ __global__ void __launch_bounds__(kThreads, RT_MINBLOCKS) draw_fast_kernel(const
   __shared__ int s_warp_count[kThreads / 32];
   __shared__ int s_base;
   __shared__ int s_spheres_visible;
+  __shared__ int s_wlist[kThreads / 32][kWarpListMax];  // per-warp shadow caster lists
 
   // ---- stage the scene: generic arrays [0,5n) and the shadow records (global offset 5n+3n_sh) ----
   float4 *const gen = smem;
   float4 *const prim = smem + 5 * n;
   float4 *const shad = prim + 3 * n;
   int *const plist = reinterpret_cast<int *>(shad + 4 * n_sh);
-  // per-thread jitter columns (SINGLE only), after the triangle list
-  float *const jit_base = reinterpret_cast<float *>(smem + scene_smem_float4(n, n_sh));
+  int *const full_list = plist + n;  // 0, 1, ..., n_sh-1: "test every caster"
+  // per-thread columns after the lists: parked primary hits (4 x 7 words), then the jitters (SINGLE only)
+  float *const rec_base = reinterpret_cast<float *>(smem + scene_smem_float4(n, n_sh));
+  float *const jit_base = rec_base + 4 * 7 * kThreads;
   for (int i = threadIdx.x; i < 5 * n; i += kThreads) gen[i] = scene[i];
   for (int i = threadIdx.x; i < 4 * n_sh; i += kThreads) shad[i] = scene[5 * n + 3 * n_sh + i];
-  if (threadIdx.x == 0) s_base = 0;
+  for (int i = threadIdx.x; i < n_sh; i += kThreads) full_list[i] = i;
   FastScene sc;
   sc.g.ta = gen;
   sc.g.tb = gen + n;
@@ -42,6 +45,7 @@ __global__ void __launch_bounds__(kThreads, RT_MINBLOCKS) draw_fast_kernel(const
   const V3<float> cam(p.cam[0], p.cam[1], p.cam[2]), light(p.light[0], p.light[1], p.light[2]);
   const int A = p.A, S = p.S;
   const float SW = (float)p.W, SH = (float)p.H, fA = (float)A;
+  if (threadIdx.x == 0) s_base = 0;
   int x, y, tile_x, tile_y;
   const bool in_frame = pixel_of_thread(p, x, y, tile_x, tile_y);
   __syncthreads();
@@ -116,7 +120,9 @@ __global__ void __launch_bounds__(kThreads, RT_MINBLOCKS) draw_fast_kernel(const
   }
   const bool spheres_visible = s_spheres_visible != 0;
 
+  const unsigned warp_mask = __ballot_sync(0xffffffffu, in_frame);  // lanes that stay for the warp collectives below
   if (!in_frame) return;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
   const int global_id = __float2int_rz(__fadd_rn(__fmul_rn((float)y, SW), (float)x));  // kernels.cl:380, float arithmetic
   // SINGLE: the pixel's S jitters, generated on the first shading point (44 % of the 1080p frame
@@ -133,39 +139,111 @@ __global__ void __launch_bounds__(kThreads, RT_MINBLOCKS) draw_fast_kernel(const
   const V3<SF> cam_s(SF(cam.x), SF(cam.y), SF(cam.z));
   V3<float> total(0.0f, 0.0f, 0.0f);
   const int rays = A * A;
-  // One primary ray at a time, in the reference's order dy*A + dx (kernels.cl:393-397); the
-  // block's binned triangle list is short, so nothing is gained by batching rays.
+  // Rays of a pixel are processed in groups of kGroup, in the reference's order dy*A + dx
+  // (kernels.cl:393-397).  Phase 1 finds the primary hit of each ray of the group and parks it in this
+  // thread's shared-memory column; phase 2 builds ONE shadow-caster list for the warp from the bounding
+  // box of all its diffuse hits of the group; phase 3 shades the parked hits.
+  constexpr int kGroup = 4, kRec = 7;  // record: id, point.xyz, normal.xyz
+  float *const rec = rec_base + threadIdx.x;
+  int ray_dx = 0, ray_dy = 0;
 #pragma unroll 1
-  for (int ray_dy = 0; ray_dy < A; ray_dy++) {
+  for (int g0 = 0; g0 < rays; g0 += kGroup) {
+    const int group = min(kGroup, rays - g0);
+    const float big = 3.0e38f;
+    V3<float> blo(big, big, big), bhi(-big, -big, -big);
+    int first_dx = ray_dx, first_dy = ray_dy;
 #pragma unroll 1
-    for (int ray_dx = 0; ray_dx < A; ray_dx++) {
+    for (int k = 0; k < group; k++) {
       const V3<SF> d0 = base + V3<SF>(SF((float)ray_dx), SF((float)ray_dy), SF(0.0f));
+      if (++ray_dx == A) {
+        ray_dx = 0;
+        ray_dy++;
+      }
       const V3<SF> dns = normalize(V3<SF>(dot(r0, d0), dot(r1, d0), dot(r2, d0)));
-      V3<float> dir(dns.x.v, dns.y.v, dns.z.v);
       int bi;
       float bt, bu, bv;
-      primary_triangles(sc, dir, bi, bt, bu, bv);
-      HitRec<float> hit;
-      {
-        HitRec<SF> hs;
-        hs.id = -1;
-        hs.color = make_float4(0.0f, 0.0f, 0.0f, 1.0f);
-        hs.point = V3<SF>(SF(0.0f), SF(0.0f), SF(0.0f));
-        hs.normal = hs.point;
-        if (bi >= 0) {
-          const V3<SF> v0 = xyz<SF>(sc.g.ta[bi]), e1 = xyz<SF>(sc.g.tb[bi]), e2 = xyz<SF>(sc.g.tc[bi]);
-          hs.id = bi;
-          hs.point = (v0 + scale(SF(bu), e1)) + scale(SF(bv), e2);  // kernels.cl:124
-          hs.normal = xyz<SF>(sc.g.tn[bi]);
-          hs.color = sc.g.tcol[bi];
-        }
-        // the two spheres, strict as well (skipped when no ray of the block's tile can reach one)
-        if (spheres_visible) closest_spheres<SF>(cam_s, dns, SF(bt), hs);
-        hit.id = hs.id;
-        hit.point = V3<float>(hs.point.x.v, hs.point.y.v, hs.point.z.v);
-        hit.normal = V3<float>(hs.normal.x.v, hs.normal.y.v, hs.normal.z.v);
-        hit.color = hs.color;
+      primary_triangles(sc, V3<float>(dns.x.v, dns.y.v, dns.z.v), bi, bt, bu, bv);
+      HitRec<SF> hs;
+      hs.id = -1;
+      hs.color = make_float4(0.0f, 0.0f, 0.0f, 1.0f);
+      hs.point = V3<SF>(SF(0.0f), SF(0.0f), SF(0.0f));
+      hs.normal = hs.point;
+      if (bi >= 0) {
+        const V3<SF> v0 = xyz<SF>(sc.g.ta[bi]), e1 = xyz<SF>(sc.g.tb[bi]), e2 = xyz<SF>(sc.g.tc[bi]);
+        hs.id = bi;
+        hs.point = (v0 + scale(SF(bu), e1)) + scale(SF(bv), e2);  // kernels.cl:124
+        hs.normal = xyz<SF>(sc.g.tn[bi]);
+        hs.color = sc.g.tcol[bi];
       }
+      // the two spheres, strict as well (skipped when no ray of the block's tile can reach one)
+      if (spheres_visible) closest_spheres<SF>(cam_s, dns, SF(bt), hs);
+      // sphere i is parked as id -2-i so that phase 3 can recover its colour (kernels.cl:28 uses -2 for both)
+      int id = hs.id;
+      if (id == -2) id = (hs.color.w == c_sphere_color[0].w) ? -2 : -3;
+      float *q = rec + k * kRec * kThreads;
+      q[0] = __int_as_float(id);
+      q[1 * kThreads] = hs.point.x.v;
+      q[2 * kThreads] = hs.point.y.v;
+      q[3 * kThreads] = hs.point.z.v;
+      q[4 * kThreads] = hs.normal.x.v;
+      q[5 * kThreads] = hs.normal.y.v;
+      q[6 * kThreads] = hs.normal.z.v;
+      if (hs.id != -1 && hs.color.w > 0.0f) {
+        blo = V3<float>(fminf(blo.x, hs.point.x.v), fminf(blo.y, hs.point.y.v), fminf(blo.z, hs.point.z.v));
+        bhi = V3<float>(fmaxf(bhi.x, hs.point.x.v), fmaxf(bhi.y, hs.point.y.v), fmaxf(bhi.z, hs.point.z.v));
+      }
+    }
+    // Phase 2 — warp-level caster cull: the diffuse primary hits of the warp's 8x4 pixels lie close
+    // together; casters that cannot shadow any point of their bounding box (walls, far faces) are dropped
+    // for the whole warp.  All lanes of warp_mask are converged here (uniform loops).
+    const int *warp_list = full_list;
+    int n_warp_list = n_sh;
+    if (n_sh <= kWarpListMax) {
+      if (__ballot_sync(warp_mask, blo.x <= bhi.x) != 0u) {
+        V3<float> lo, hi;
+        lo.x = float_of_ord(__reduce_min_sync(warp_mask, ord_of_float(blo.x)));
+        lo.y = float_of_ord(__reduce_min_sync(warp_mask, ord_of_float(blo.y)));
+        lo.z = float_of_ord(__reduce_min_sync(warp_mask, ord_of_float(blo.z)));
+        hi.x = float_of_ord(__reduce_max_sync(warp_mask, ord_of_float(bhi.x)));
+        hi.y = float_of_ord(__reduce_max_sync(warp_mask, ord_of_float(bhi.y)));
+        hi.z = float_of_ord(__reduce_max_sync(warp_mask, ord_of_float(bhi.z)));
+        // the casters are dealt out to the lanes that are present (edge warps have fewer than 32)
+        const int n_act = __popc(warp_mask), rank = __popc(warp_mask & ((1u << lane) - 1u));
+        int count = 0;
+        for (int c0 = 0; c0 < n_sh; c0 += n_act) {
+          const int c = c0 + rank;
+          const bool keep = c < n_sh && box_may_be_shadowed_by(shad, c, lo, hi, light);
+          const unsigned bal = __ballot_sync(warp_mask, keep);
+          if (keep) s_wlist[warp][count + __popc(bal & ((1u << lane) - 1u))] = c;
+          count += __popc(bal);
+        }
+        __syncwarp(warp_mask);
+        warp_list = s_wlist[warp];
+        n_warp_list = count;
+      }
+    }
+    // Phase 3 — shade the parked hits
+#pragma unroll 1
+    for (int k = 0; k < group; k++) {
+      const float *q = rec + k * kRec * kThreads;
+      HitRec<float> hit;
+      hit.id = __float_as_int(q[0]);
+      hit.point = V3<float>(q[1 * kThreads], q[2 * kThreads], q[3 * kThreads]);
+      hit.normal = V3<float>(q[4 * kThreads], q[5 * kThreads], q[6 * kThreads]);
+      hit.color = make_float4(0.0f, 0.0f, 0.0f, 1.0f);
+      if (hit.id >= 0) hit.color = sc.g.tcol[hit.id];
+      else if (hit.id <= -2) hit.color = c_sphere_color[-2 - hit.id];
+      V3<float> dir(0.0f, 0.0f, 0.0f);
+      if (hit.id != -1 && hit.color.w <= 0.0f) {
+        // mirror / glass: the bounce needs the ray direction again (same strict sequence as phase 1)
+        const int idx = first_dy * A + first_dx + k;
+        const int ddy = idx / A, ddx = idx - ddy * A;
+        const V3<SF> d0 = base + V3<SF>(SF((float)ddx), SF((float)ddy), SF(0.0f));
+        const V3<SF> dns = normalize(V3<SF>(dot(r0, d0), dot(r1, d0), dot(r2, d0)));
+        dir = V3<float>(dns.x.v, dns.y.v, dns.z.v);
+      }
+      sc.clist = warp_list;
+      sc.n_clist = n_warp_list;
       // direct light of a diffuse hit, or secondary_light's bounce loop (kernels.cl:342-365) ending in
       // the same shading — a single call site for both
       float medium = RT_AIR, gain = 1.0f;
@@ -194,6 +272,8 @@ __global__ void __launch_bounds__(kThreads, RT_MINBLOCKS) draw_fast_kernel(const
         hit.color.w = 1.0f;
         closest_hit<float>(sc.g, start, dir, hit);
         gain = 0.9f;
+        sc.clist = full_list;  // the warp list was built for the primary hits only
+        sc.n_clist = n_sh;
       }
     }
   }
@@ -206,7 +286,7 @@ __global__ void __launch_bounds__(kThreads, RT_MINBLOCKS) draw_fast_kernel(const
 
 cudaError_t RT_CAT(launch_fast_ch, RT_FAST_CH)(rt_ctx *ctx, const FrameParams &fp, cudaStream_t stream) {
   constexpr int CH = RT_FAST_CH;
-  ctx->launch_extra_smem = sizeof(float) * 3 * CH * kThreads;  // jitter columns
+  ctx->launch_extra_smem = sizeof(float) * (3 * CH + 4 * 7) * kThreads;  // jitter columns + parked primary hits
   if (fp.S == CH) return launch_kernel(draw_fast_kernel<CH, true>, ctx, fp, stream);
   return launch_kernel(draw_fast_kernel<CH, false>, ctx, fp, stream);
 }

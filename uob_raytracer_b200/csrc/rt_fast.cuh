@@ -57,7 +57,51 @@ struct FastScene {
   const float4 *shad;   // 4 per shadow caster
   const int *plist;     // triangles surviving the block's binning, ascending
   int n_prim;           // entries in plist
+  const int *clist;     // shadow casters to test for the current shading point (warp list or all)
+  int n_clist;
 };
+
+constexpr int kWarpListMax = 64;  // per-warp caster lists are kept for scenes with at most this many casters
+
+// Monotonic float -> unsigned map, so that warp-wide min/max can use the integer REDUX unit.
+__device__ __forceinline__ unsigned ord_of_float(float f) {
+  const unsigned u = __float_as_uint(f);
+  return u ^ ((u >> 31) ? 0xffffffffu : 0x80000000u);
+}
+__device__ __forceinline__ float float_of_ord(unsigned o) {
+  return __uint_as_float(o ^ ((o >> 31) ? 0x80000000u : 0xffffffffu));
+}
+
+// Warp-level version of the plane cull of shadow_lit_count: can caster `c` be hit by a shadow ray
+// from ANY point of the box [lo,hi] (the bounding box of the warp's 8x4 shading points)?
+// num(P) = (P + bias (L-P) - v0).N and rN(P) = (L-P).N are affine in P, so over the box they stay within
+// +-hN of their centre values, hN = |N|.half-extent; |r|/|d_s| <= k(R) is largest at the box point
+// nearest to the light.  False only if the per-point cull would reject the pair at every point.
+__device__ __forceinline__ bool box_may_be_shadowed_by(const float4 *shad, int c, V3<float> lo, V3<float> hi, V3<float> light) {
+  const float4 Q0 = shad[4 * c], Q1 = shad[4 * c + 1];
+  const V3<float> ctr((lo.x + hi.x) * 0.5f, (lo.y + hi.y) * 0.5f, (lo.z + hi.z) * 0.5f);
+  const V3<float> half((hi.x - lo.x) * 0.5f, (hi.y - lo.y) * 0.5f, (hi.z - lo.z) * 0.5f);
+  const V3<float> r(light.x - ctr.x, light.y - ctr.y, light.z - ctr.z);
+  const V3<float> b(ctr.x + RT_BIAS * r.x - Q0.x, ctr.y + RT_BIAS * r.y - Q0.y, ctr.z + RT_BIAS * r.z - Q0.z);
+  const float num = (b.x * Q1.x - b.y * Q1.y) + b.z * Q1.z;
+  const float rN = (r.x * Q1.x - r.y * Q1.y) + r.z * Q1.z;
+  const float hN = 1.0001f * (fabsf(Q1.x) * half.x + fabsf(Q1.y) * half.y + fabsf(Q1.z) * half.z) + 1e-7f * (fabsf(num) + fabsf(rN));
+  // nearest distance from the light to the box
+  const float dx = fmaxf(fmaxf(lo.x - light.x, light.x - hi.x), 0.0f), dy = fmaxf(fmaxf(lo.y - light.y, light.y - hi.y), 0.0f),
+              dz = fmaxf(fmaxf(lo.z - light.z, light.z - hi.z), 0.0f);
+  const float rmin = sqrtf(dx * dx + dy * dy + dz * dz) * 0.9999f;
+  if (!(rmin > 2.0f * kJitterMax)) return true;
+  const float kk = kSlack * rmin / (rmin - kJitterMax);
+  if (num - hN > 0.0f) {        // every point is on the + side of the plane
+    const float rhs = Q0.w - (rN - hN);
+    return !(rhs <= 0.0f || (num - hN) >= rhs * kk);
+  }
+  if (num + hN < 0.0f) {        // every point is on the - side
+    const float rhs = Q0.w + (rN + hN);
+    return !(rhs <= 0.0f || -(num + hN) >= rhs * kk);
+  }
+  return true;
+}
 
 __device__ __forceinline__ float xor_sign(float v, unsigned signbit) { return __uint_as_float(__float_as_uint(v) ^ signbit); }
 
@@ -206,9 +250,8 @@ __device__ __forceinline__ int shadow_lit_count(const FastScene &sc, V3<float> s
   const float inv_r2 = rcp_approx(radius_sq);
   const float kk = (R > 2.0f * kJitterMax) ? kSlack * R * rcp_approx(R - kJitterMax) : 1e30f;
 
-  const float4 *q = sc.shad;
-  const float4 *const q_end = q + 4 * sc.g.n_sh;
-  for (; q < q_end; q += 4) {
+  for (int l = 0; l < sc.n_clist; l++) {
+    const float4 *q = sc.shad + 4 * sc.clist[l];
     const float4 Q0 = q[0], Q1 = q[1];
     const V3<float> b(start.x - Q0.x, start.y - Q0.y, start.z - Q0.z);
     const float c0 = Q1.x, c1 = Q1.y, c2 = Q1.z;

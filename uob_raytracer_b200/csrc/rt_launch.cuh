@@ -46,7 +46,7 @@ __device__ __forceinline__ bool pixel_of_thread(const FrameParams &p, int &x, in
 
 
 // float4 slots of the scene part of the fast kernel's shared memory (see brute_smem_bytes)
-__host__ __device__ inline int scene_smem_float4(int n, int n_sh) { return 8 * n + 4 * n_sh + (n + 3) / 4 + 1; }
+__host__ __device__ inline int scene_smem_float4(int n, int n_sh) { return 8 * n + 4 * n_sh + (n + n_sh + 3) / 4 + 1; }
 
 template <class K>
 inline cudaError_t launch_kernel(K kern, rt_ctx *ctx, const FrameParams &fp_in, cudaStream_t stream) {
