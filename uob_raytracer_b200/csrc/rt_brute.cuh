@@ -81,18 +81,45 @@ __device__ __forceinline__ void closest_tri_test(float4 A, float4 Bq, float4 C, 
   const V3<T> v0 = xyz<T>(A), e1 = xyz<T>(Bq), e2 = xyz<T>(C);
   const T c0 = T(A.w), c1 = T(Bq.w), c2 = T(C.w);
   const V3<T> b = start - v0;
-  const T detA = (nd.x * c0 - nd.y * c1) + nd.z * c2;
-  const T inv = rcp_(detA);
-  const T t = ((b.x * c0 - b.y * c1) + b.z * c2) * inv;
-  const T u = ((nd.x * (b.y * e2.z - b.z * e2.y) - nd.y * (b.x * e2.z - b.z * e2.x)) + nd.z * (b.x * e2.y - b.y * e2.x)) * inv;
-  const T v = ((nd.x * (e1.y * b.z - e1.z * b.y) - nd.y * (e1.x * b.z - e1.z * b.x)) + nd.z * (e1.x * b.y - e1.y * b.x)) * inv;
-  const bool closer = ORDERED ? (t < cs.t) : ((t < cs.t) || (t == cs.t && id < cs.id));
-  if (closer && u >= T(0.0f) && v >= T(0.0f) && (u + v) <= T(1.0f) && t >= T(0.0f)) {
-    cs.id = id;
-    cs.slot = slot;
-    cs.u = u;
-    cs.v = v;
-    cs.t = t;
+  if constexpr (is_strict<T>::value) {
+    const T detA = (nd.x * c0 - nd.y * c1) + nd.z * c2;
+    const T inv = rcp_(detA);
+    const T t = ((b.x * c0 - b.y * c1) + b.z * c2) * inv;
+    const T u = ((nd.x * (b.y * e2.z - b.z * e2.y) - nd.y * (b.x * e2.z - b.z * e2.x)) + nd.z * (b.x * e2.y - b.y * e2.x)) * inv;
+    const T v = ((nd.x * (e1.y * b.z - e1.z * b.y) - nd.y * (e1.x * b.z - e1.z * b.x)) + nd.z * (e1.x * b.y - e1.y * b.x)) * inv;
+    const bool closer = ORDERED ? (t < cs.t) : ((t < cs.t) || (t == cs.t && id < cs.id));
+    if (closer && u >= T(0.0f) && v >= T(0.0f) && (u + v) <= T(1.0f) && t >= T(0.0f)) {
+      cs.id = id;
+      cs.slot = slot;
+      cs.u = u;
+      cs.v = v;
+      cs.t = t;
+    }
+  } else {
+    // Fast policy: the same quantities through scalar triple products, deciding the inside test on
+    // numerators and dividing only for a triangle that passes it.  With d = -nd, q = b x d:
+    //   det A = -d.N = -dn,  det[b,e1,e2] = b.N,  det[-d,b,e2] = e2.q,  det[-d,e1,b] = -e1.q
+    //   t = -(b.N)/dn,  u = -(e2.q)/dn,  v = (e1.q)/dn
+    const V3<T> d = -nd;
+    const float dn = (d.x * c0 - d.y * c1) + d.z * c2;
+    const float bn = (b.x * c0 - b.y * c1) + b.z * c2;
+    const V3<T> q(b.y * d.z - b.z * d.y, b.z * d.x - b.x * d.z, b.x * d.y - b.y * d.x);
+    const float eu = -dot(e2, q), ev = dot(e1, q);
+    const unsigned sb = __float_as_uint(dn) & 0x80000000u;
+    const float us = __uint_as_float(__float_as_uint(eu) ^ sb), vs = __uint_as_float(__float_as_uint(ev) ^ sb),
+                ts = __uint_as_float(__float_as_uint(-bn) ^ sb), adn = fabsf(dn);
+    if ((us >= 0.0f) & (vs >= 0.0f) & ((us + vs) <= adn) & (ts >= 0.0f)) {
+      const float inv = __frcp_rn(adn);
+      const float t = ts * inv;
+      const bool closer = ORDERED ? (t < cs.t) : ((t < cs.t) || (t == cs.t && id < cs.id));
+      if (closer) {
+        cs.id = id;
+        cs.slot = slot;
+        cs.u = us * inv;
+        cs.v = vs * inv;
+        cs.t = t;
+      }
+    }
   }
 }
 

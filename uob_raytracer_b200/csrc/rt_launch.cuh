@@ -35,7 +35,8 @@ __device__ __forceinline__ SceneView stage_scene(float4 *smem, const float4 *__r
 // Pixel tile of this block (top-left corner) and pixel of this thread; false if outside the frame rows.
 __device__ __forceinline__ bool pixel_of_thread(const FrameParams &p, int &x, int &y, int &tile_x, int &tile_y) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int gb = blockIdx.x * p.blk_stride + p.blk_phase;
+  int gb = blockIdx.x * p.blk_stride + p.blk_phase;
+  if (p.tile_order) gb = p.tile_order[gb];
   const int by = gb / p.grid_x, bx = gb - by * p.grid_x;
   tile_x = bx * kTileW;
   tile_y = p.row0 + by * kTileH;
@@ -44,6 +45,9 @@ __device__ __forceinline__ bool pixel_of_thread(const FrameParams &p, int &x, in
   return x < p.W && y < p.row0 + p.rows;
 }
 
+
+// rt_api.cu: device table of the launch order for a (row0, rows) range, built on first use
+const int *tile_order_for(rt_ctx *ctx, int row0, int rows, int grid_x, int n_blocks);
 
 // float4 slots of the scene part of the fast kernel's shared memory (see brute_smem_bytes)
 __host__ __device__ inline int scene_smem_float4(int n, int n_sh) { return 8 * n + 4 * n_sh + (n + n_sh + 3) / 4 + 1; }
@@ -55,6 +59,7 @@ inline cudaError_t launch_kernel(K kern, rt_ctx *ctx, const FrameParams &fp_in, 
   fp.n_blocks = fp.grid_x * ((fp.rows + kTileH - 1) / kTileH);
   fp.blk_stride = ctx->cfg.block_stride > 1 ? ctx->cfg.block_stride : 1;
   fp.blk_phase = ctx->cfg.block_stride > 1 ? ctx->cfg.block_phase : 0;
+  fp.tile_order = tile_order_for(ctx, fp.row0, fp.rows, fp.grid_x, fp.n_blocks);
   const int my_blocks = (fp.n_blocks - fp.blk_phase + fp.blk_stride - 1) / fp.blk_stride;
   const size_t smem = brute_smem_bytes(ctx->n, ctx->n_sh) + ctx->launch_extra_smem;
   ctx->launch_extra_smem = 0;

@@ -13,6 +13,9 @@ struct FrameParams {
   // 16 x kTileH pixel blocks of those rows are numbered row-major; this launch renders the blocks
   // gb = b*blk_stride + blk_phase (b = blockIdx.x): 1/0 = all of them, N/g = rank g of an N-way interleave
   int blk_stride, blk_phase, grid_x, n_blocks;
+  // optional launch order: tile_order[k] = row-major block number of the k-th block to start
+  // (expensive centre tiles first, so that no long-running block is left for the tail)
+  const int *tile_order;
   int A, S, B;     // AA edge, shadow samples, max bounces
   float focal;
   float rot[9];    // rows r0, r1, r2 (skeleton.cpp:149-151)
