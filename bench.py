@@ -114,11 +114,37 @@ class ClockSampler:
                 "power_w_max": max(power) if power else None, "samples": len(sm), "reasons": sorted(reasons)}
 
 
-def scene_and_camera():
+_scene_cache = {}
+
+
+def scene_and_camera(workload: str = "cfg2"):
+    """Cornell box (+ for cfg4 the 1,310,720-face icosphere loaded through load_obj, appended as
+    skeleton.cpp:102-103 would) and the reference's default camera / light."""
     import uob_raytracer_b200 as u
-    scene = u.load_test_model()
+    mesh = workload == "cfg4"
+    if mesh not in _scene_cache:
+        scene = u.load_test_model()
+        if mesh:
+            import tempfile
+            path = os.path.join(tempfile.gettempdir(), f"uob_ico8_{os.getpid()}.obj")
+            u.write_icosphere_obj(path, 8, 0.2, 0.05)
+            scene = scene + u.load_obj(path)
+            os.unlink(path)
+        _scene_cache[mesh] = scene
     cam = u.Camera()
-    return scene, cam.rot(), cam.position.copy(), cam.light.copy()
+    return _scene_cache[mesh], cam.rot(), cam.position.copy(), cam.light.copy()
+
+
+def gpu_ray_counts(cfg, scene, rot, cam4, light4, device=0, row0=0, rows=0) -> dict:
+    """Ray counts from the strict kernel's counters (RT_FLAG_COUNT_RAYS) — equal to the oracle's counters on every
+    config the oracle can run (tests/test_gpu_parity.py::test_ray_counters_equal_the_oracle); used where the
+    oracle cannot run (1.3 M triangles: ~0.1 core-second per pixel)."""
+    import uob_raytracer_b200 as u
+    with u.Renderer(cfg.width, cfg.height, cfg.aa, cfg.shadow_samples, cfg.max_bounces, device=device, strict=True,
+                    count_rays=True, row0=row0, rows=rows) as r:
+        r.upload_scene(scene)
+        r.render(rot, cam4, light4, cfg.focal)
+        return r.ray_counts()
 
 
 def cpu_reference_frame(cfg, rows_step: int, threads: int = 0):
@@ -126,7 +152,20 @@ def cpu_reference_frame(cfg, rows_step: int, threads: int = 0):
     Returns (seconds, rays traced, kind)."""
     from oracle import bind as ob
     import uob_raytracer_b200 as u
-    scene, rot, cam4, light4 = scene_and_camera()
+    scene, rot, cam4, light4 = scene_and_camera(cfg.name)
+    if cfg.name == "cfg4":
+        # Brute force over 1.3 M triangles costs ~25 ms per ray per core, so the CPU sample is ONE row through the
+        # mesh of the same scene and camera at quarter resolution (480x270, focal scaled): ~20 k rays, ~30 s on 16 cores.
+        from uob_raytracer_b200.configs import RenderConfig
+        small = RenderConfig("cfg4-sample", cfg.width // 4, cfg.height // 4, cfg.aa, cfg.shadow_samples, cfg.max_bounces, "")
+        y0 = small.height // 2
+        rays = gpu_ray_counts(small, scene, rot, cam4, light4, row0=y0, rows=1)["rays"]
+        t0 = time.perf_counter()
+        kind = "reference" if ob.ref_available(cfg.aa, cfg.shadow_samples, cfg.max_bounces) else "port"
+        fn = ob.ref_render if kind == "reference" else ob.oracle_render
+        fn(small.width, small.height, small.aa, small.shadow_samples, small.max_bounces, small.focal, scene.verts, scene.normals,
+           scene.colors, rot, cam4, light4, y0=y0, y1=y0 + 1, threads=threads)
+        return time.perf_counter() - t0, rays, kind
     counts = load_counts(cfg.name)
     if rows_step == 1:
         rays = counts["rays"]
@@ -147,6 +186,8 @@ def cpu_reference_frame(cfg, rows_step: int, threads: int = 0):
 
 def pick_row_step(cfg) -> int:
     """Bound the CPU sample: a full frame when it takes < ~3 s on this host, else every k-th row."""
+    if cfg.name == "cfg4":
+        return 540  # fixed two-row sample, see cpu_reference_frame
     t, _, _ = cpu_reference_frame(cfg, 16)
     full = t * 16
     step = 1
@@ -204,8 +245,13 @@ def run_ours(args, cfg) -> int:
     W, H = cfg.width, cfg.height
     from uob_raytracer_b200 import tiles
     row0, rows = tiles.row_tile(H, world, rank)
-    counts = load_counts(cfg.name)
-    scene, rot, cam4, light4 = scene_and_camera()
+    scene, rot, cam4, light4 = scene_and_camera(cfg.name)
+    if cfg.name == "cfg4":
+        counts = gpu_ray_counts(cfg, scene, rot, cam4, light4, device=local_rank)
+        rays_source = "strict-kernel ray counters (RT_FLAG_COUNT_RAYS; equal to the oracle's on cfg1/cfg2 — the oracle cannot run 1.3 M triangles)"
+    else:
+        counts = load_counts(cfg.name)
+        rays_source = "oracle counters (tests/golden/ray_counts.json)"
 
     # Multi-GPU gather of the frame on rank 0:
     #   nccl: contiguous row tiles, in-place NCCL all-gather into every rank's frame (the north-star path)
@@ -340,7 +386,8 @@ def run_ours(args, cfg) -> int:
     if rank == 0:
         ms_per_step = total_step_ms / args.steps
         kern_ms_per_step = total_kern_ms / args.steps
-        flops = algorithmic_flops(counts) / world  # per launch (one rank's tile; tiles are near-uniform)
+        mesh = cfg.name == "cfg4"
+        flops = 0.0 if mesh else algorithmic_flops(counts) / world  # per launch (one rank's tile; tiles are near-uniform)
         achieved = flops / (kern_ms_per_step * 1e-3) / 1e12
         nominal = 148 * 128 * 2 * 1.965e9 / 1e12
         line = {
@@ -349,7 +396,7 @@ def run_ours(args, cfg) -> int:
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": cfg.name, "description": cfg.description, "width": W, "height": H, "aa": cfg.aa,
                        "shadow_samples": cfg.shadow_samples, "max_bounces": cfg.max_bounces, "focal": cfg.focal,
-                       "rays_per_frame": counts["rays"], "rays_source": "oracle counters (tests/golden/ray_counts.json)",
+                       "rays_per_frame": counts["rays"], "rays_source": rays_source, "triangles": scene.n,
                        "partition": (f"{world} row tile(s) of {rows} rows" + (", in-place NCCL all-gather per frame" if world > 1 else ""))
                        if gather != "p2p" else f"16x16-pixel blocks interleaved over {world} ranks, peer stores into rank 0's frame over NVLink + 4-byte all-reduce per frame",
                        "gather": gather,
@@ -361,7 +408,7 @@ def run_ours(args, cfg) -> int:
             "e2e": e2e_line,
             "gpu_launches": int(launches),
             "clocks": clocks,
-            "roofline": {"bound": "fp32", "kernel": "draw_fast_kernel<%d,%d,true>" % (10 if cfg.shadow_samples % 10 == 0 else 8, 4 if (cfg.aa * cfg.aa) % 4 == 0 else 1),
+            "roofline": {"bound": "fp32", "kernel": "draw_fast_kernel<%d,true>" % (10 if cfg.shadow_samples % 10 == 0 else 8),
                          "achieved": round(achieved, 3), "peak": round(fp32_peak, 3), "unit": "TFLOP/s",
                          "frac": round(achieved / fp32_peak, 4) if fp32_peak else None,
                          "peak_source": "FFMA microbenchmark in this run (rt_measure_fp32_peak); MEASURED_PEAKS.json has no FP32 entry",
@@ -369,21 +416,38 @@ def run_ours(args, cfg) -> int:
                          "algorithmic_gflop_per_launch": round(flops / 1e9, 3),
                          "traffic": load_traffic(cfg.name)},
         }
+        if mesh:
+            # BVH path: no FLOP bound.  Algorithmic bytes: a binary BVH with 4-triangle leaves needs
+            # ceil(log2(N/4)) = 19 node visits x 64 B + 4 triangles x 48 B = 1.4 KB per ray.
+            bytes_per_ray = 19 * 64 + 4 * 48
+            peaks = {}
+            try:
+                with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+                    peaks = json.load(f)
+            except Exception:
+                pass
+            peak = float(peaks.get("hbm_gbs", 6650.0))
+            ach = bytes_per_ray * counts["rays"] / world / (kern_ms_per_step * 1e-3) / 1e9
+            line["roofline"] = {"bound": "hbm", "kernel": "draw_bvh_kernel<float,8>", "achieved": round(ach, 1), "peak": peak,
+                                "unit": "GB/s", "frac": round(ach / peak, 4),
+                                "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 GB/s (of fallback)",
+                                "algorithmic_bytes_per_ray": bytes_per_ray, "traffic": load_traffic(cfg.name),
+                                "note": "latency / L2-bound traversal: nodes 42 MB + triangles 63 MB fit the 126 MB L2"}
         # CPU baseline on this box's host cores (N = 1 only)
         if world == 1 and not args.no_cpu_baseline:
             step = pick_row_step(cfg)
             best, rays, kind = None, 0, "reference"
             t_budget = time.perf_counter()
-            for i in range(6):
+            for i in range(1 if mesh else 6):
                 t, rays, kind = cpu_reference_frame(cfg, step)
                 best = t if best is None else min(best, t)
                 if time.perf_counter() - t_budget > 15.0:
                     break
             line["cpu_baseline"] = {
                 "value": round(rays / best / 1e6, 2), "unit": UNIT, "cores": os.cpu_count(), "kind": kind,
-                "sample": f"{cfg.name}, " + ("all rows" if step == 1 else f"every {step}th row") +
+                "sample": ("cfg4 scene at 480x270, one row through the mesh" if mesh else f"{cfg.name}, " + ("all rows" if step == 1 else f"every {step}th row")) +
                           f", best of {i + 1} frames; verbatim kernels.cl via g++ shim (-O2, strict IEEE), all host threads",
-                "ms_per_frame": round(best * step * 1e3, 1)}
+                "ms_per_frame": None if mesh else round(best * step * 1e3, 1)}
         print(json.dumps(line), flush=True)
     if peer_ptr:
         torch.cuda.synchronize()

@@ -41,7 +41,10 @@ enum {
    * division-free shadow tests), within 1/255 on >= 99.9 % of pixels. */
   RT_FLAG_STRICT_IEEE = 1u << 0,
   RT_FLAG_FORCE_BRUTE = 1u << 1, /* never build a BVH, whatever the triangle count */
-  RT_FLAG_FORCE_BVH = 1u << 2    /* always traverse a BVH, even for 26 triangles */
+  RT_FLAG_FORCE_BVH = 1u << 2,   /* always traverse a BVH, even for 26 triangles */
+  /* Count the rays of every frame (rt_get_ray_counts).  Measurement aid: frames are rendered by the
+   * generic kernel (same pixels), not the tuned one, so do not time a counting context. */
+  RT_FLAG_COUNT_RAYS = 1u << 3
 };
 
 /* Everything that is a compile-time constant in the reference
@@ -128,6 +131,12 @@ void rt_destroy(rt_ctx *ctx);
 
 /* Last error message of ctx (or of rt_create when ctx == NULL). Never NULL. */
 const char *rt_last_error(const rt_ctx *ctx);
+
+/* Rays traced by the last frame of a RT_FLAG_COUNT_RAYS context: {primary, shadow, bounce}, with
+ * the definition of SURVEY.md §8d (one ray = one closest-hit search or one in_shadow call).  Under
+ * RT_FLAG_STRICT_IEEE the counts equal the CPU oracle's counters exactly (tests); this is where the
+ * ray count of scenes too large for the oracle (1.3 M triangles) comes from. */
+int rt_get_ray_counts(rt_ctx *ctx, uint64_t counts[3]);
 
 /* Diagnostic: measured FP32 FFMA throughput of this device in TFLOP/s (dependent-chain-free
  * FFMA microbenchmark, best of 5, CUDA events) — the roofline denominator bench.py reports

@@ -23,6 +23,7 @@ RT_OK, RT_ERR_INVALID, RT_ERR_CUDA, RT_ERR_NO_SCENE, RT_ERR_NO_DEVICE = range(5)
 RT_FLAG_STRICT_IEEE = 1 << 0
 RT_FLAG_FORCE_BRUTE = 1 << 1
 RT_FLAG_FORCE_BVH = 1 << 2
+RT_FLAG_COUNT_RAYS = 1 << 3
 
 
 class RtConfig(ctypes.Structure):
@@ -49,6 +50,7 @@ RT_SYMBOLS = {
     "rt_scene_mode": (ctypes.c_char_p, [ctypes.c_void_p]),
     "rt_destroy": (None, [ctypes.c_void_p]),
     "rt_last_error": (ctypes.c_char_p, [ctypes.c_void_p]),
+    "rt_get_ray_counts": (ctypes.c_int, [ctypes.c_void_p, ctypes.POINTER(ctypes.c_uint64)]),
     "rt_measure_fp32_peak": (ctypes.c_int, [ctypes.c_void_p, c_float_p]),
     "rt_enable_peer": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int]),
     "rt_ipc_export_frame": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p]),

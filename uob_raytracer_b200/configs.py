@@ -25,5 +25,6 @@ CONFIGS = {
     "cfg1": RenderConfig("cfg1", 1024, 1024, 1, 1, 0, "Cornell Box, default resolution, 1 spp, direct light only"),
     "cfg2": RenderConfig("cfg2", 1920, 1080, 2, 8, 10, "Cornell Box 1080p, reflection/refraction, 8-sample soft shadows, 4x AA"),
     "cfg3": RenderConfig("cfg3", 3840, 2160, 4, 10, 4, "Cornell Box 4K, 16 spp AA, soft shadows, 4 bounces"),
+    "cfg4": RenderConfig("cfg4", 1920, 1080, 2, 8, 10, "Loader.cpp synthetic 1.31 M-triangle OBJ mesh (icosphere, 8 subdivisions) inside the Cornell Box, GPU-built BVH, 1080p"),
     "cfg5": RenderConfig("cfg5", 7680, 4320, 2, 10, 10, "8K frame of the full-feature Cornell Box"),
 }

@@ -86,6 +86,7 @@ static int free_ctx(rt_ctx *ctx) {
   if (ctx->own_stream && ctx->own_stream != ctx->stream) cudaStreamSynchronize(ctx->own_stream);
   if (ctx->d_frame) cudaFree(ctx->d_frame);
   if (ctx->d_scene) cudaFree(ctx->d_scene);
+  if (ctx->d_ray_counters) cudaFree(ctx->d_ray_counters);
   for (auto &t : ctx->tile_orders) cudaFree(t.d_order);
   rt::bvh_free(ctx);
   for (int b = 0; b < rt_ctx::kBands; b++) {
@@ -161,6 +162,11 @@ rt_ctx *rt_create(const rt_config *cfg) {
   if ((e = cudaEventCreateWithFlags(&ctx->band_start, cudaEventDisableTiming)) != cudaSuccess) return fail("creating event", e);
   if ((e = cudaMalloc(&ctx->d_frame, sizeof(uint32_t) * (size_t)cfg->width * cfg->height)) != cudaSuccess)
     return fail("creating screen buffer", e);
+  if (cfg->flags & RT_FLAG_COUNT_RAYS) {
+    if ((e = cudaMalloc(&ctx->d_ray_counters, 3 * sizeof(unsigned long long))) != cudaSuccess) return fail("creating ray counters", e);
+    if ((e = cudaMemsetAsync(ctx->d_ray_counters, 0, 3 * sizeof(unsigned long long), ctx->stream)) != cudaSuccess)
+      return fail("clearing ray counters", e);
+  }
   if ((e = cudaMemsetAsync(ctx->d_frame, 0, sizeof(uint32_t) * (size_t)cfg->width * cfg->height, ctx->stream)) != cudaSuccess)
     return fail("clearing screen buffer", e);
   return ctx;
@@ -274,6 +280,9 @@ static int render_impl(rt_ctx *ctx, const float rot12[12], const float cam[4], c
     fp.light[c] = light[c];
   }
   fp.out = dev_argb ? dev_argb : ctx->d_frame;
+  fp.ray_counters = ctx->d_ray_counters;
+  if (ctx->d_ray_counters && band_row0 < 0)
+    RT_CUDA(ctx, cudaMemsetAsync(ctx->d_ray_counters, 0, 3 * sizeof(unsigned long long), stream), "clearing ray counters");
   const bool whole = band_row0 < 0;
   if (whole) RT_CUDA(ctx, cudaEventRecord(ctx->ev0, stream), "recording start event");
   RT_CUDA(ctx, ctx->use_bvh ? rt::launch_draw_bvh(ctx, fp, stream) : rt::launch_draw_brute(ctx, fp, stream), "enqueueing draw kernel");
@@ -300,7 +309,7 @@ int rt_render(rt_ctx *ctx, const float rot12[12], const float cam[4], const floa
   // Band height: a multiple of the block height, about a quarter of the tile.  Small tiles and
   // block-interleaved contexts (whose frame is completed by other GPUs) render in one piece.
   int band_rows = ((ctx->rows + rt_ctx::kBands - 1) / rt_ctx::kBands + 15) / 16 * 16;
-  if (ctx->rows < 256 || ctx->cfg.block_stride > 1) band_rows = ctx->rows;
+  if (ctx->rows < 256 || ctx->cfg.block_stride > 1 || ctx->d_ray_counters) band_rows = ctx->rows;
   if (band_rows >= ctx->rows) {
     int rc = render_impl(ctx, rot12, cam, light, focal, nullptr, ctx->stream);
     if (rc != RT_OK) return rc;
@@ -386,6 +395,20 @@ int rt_ipc_close_frame(rt_ctx *ctx, uint32_t *dev_argb) {
   RT_CUDA(ctx, cudaSetDevice(ctx->cfg.device), "selecting device");
   RT_CUDA(ctx, cudaStreamSynchronize(ctx->stream), "waiting for the stream");
   RT_CUDA(ctx, cudaIpcCloseMemHandle(dev_argb), "unmapping the peer frame buffer");
+  return RT_OK;
+}
+
+int rt_get_ray_counts(rt_ctx *ctx, uint64_t counts[3]) {
+  if (!ctx || !counts) return RT_ERR_INVALID;
+  if (!ctx->d_ray_counters) {
+    ctx->err = "rt_get_ray_counts: the context was not created with RT_FLAG_COUNT_RAYS";
+    return RT_ERR_INVALID;
+  }
+  RT_CUDA(ctx, cudaSetDevice(ctx->cfg.device), "selecting device");
+  unsigned long long h[3];
+  RT_CUDA(ctx, cudaMemcpyAsync(h, ctx->d_ray_counters, sizeof h, cudaMemcpyDeviceToHost, ctx->stream), "reading ray counters");
+  RT_CUDA(ctx, cudaStreamSynchronize(ctx->stream), "reading ray counters");
+  for (int i = 0; i < 3; i++) counts[i] = h[i];
   return RT_OK;
 }
 

@@ -398,6 +398,7 @@ __device__ __forceinline__ uint32_t shade_pixel(const Tracer &tr, const FramePar
   const V3<T> r0(T(p.rot[0]), T(p.rot[1]), T(p.rot[2])), r1(T(p.rot[3]), T(p.rot[4]), T(p.rot[5])), r2(T(p.rot[6]), T(p.rot[7]), T(p.rot[8]));
   const V3<T> cam(T(p.cam[0]), T(p.cam[1]), T(p.cam[2])), light(T(p.light[0]), T(p.light[1]), T(p.light[2]));
   V3<T> total(T(0.0f), T(0.0f), T(0.0f));
+  unsigned n_shadow_calls = 0u, n_bounce = 0u;  // ray statistics (only reported with RT_FLAG_COUNT_RAYS)
 #pragma unroll 1
   for (int dy = 0; dy < A; dy++) {
 #pragma unroll 1
@@ -414,6 +415,7 @@ __device__ __forceinline__ uint32_t shade_pixel(const Tracer &tr, const FramePar
       while (hit.id != -1) {
         if (hit.color.w > 0.0f) {
           const V3<T> dl = direct_light<T, CH, Tracer>(tr, hit.point, hit.normal, light, p.S, global_id);
+          n_shadow_calls++;
           const V3<T> lightv(T(RT_INDIRECT) + dl.x, T(RT_INDIRECT) + dl.y, T(RT_INDIRECT) + dl.z);
           // primary: colour*(indirect + direct) (kernels.cl:422); after a bounce: 0.9*light*colour (:355)
           total = total + (bounced ? scale(T(0.9f), lightv) * xyz<T>(hit.color) : xyz<T>(hit.color) * lightv);
@@ -428,9 +430,15 @@ __device__ __forceinline__ uint32_t shade_pixel(const Tracer &tr, const FramePar
         hit.id = -1;
         hit.color.w = 1.0f;
         tr.closest(start, dir, hit);
+        n_bounce++;
         bounced = true;
       }
     }
+  }
+  if (p.ray_counters) {
+    atomicAdd(p.ray_counters + 0, (unsigned long long)(A * A));
+    atomicAdd(p.ray_counters + 1, (unsigned long long)n_shadow_calls * (unsigned long long)p.S);
+    atomicAdd(p.ray_counters + 2, (unsigned long long)n_bounce);
   }
   const T fa = T(__int2float_rn(A * A));
   return pack_argb<T>(V3<T>(div_(total.x, fa), div_(total.y, fa), div_(total.z, fa)));

@@ -47,6 +47,10 @@ cudaError_t launch_draw_brute(rt_ctx *ctx, const FrameParams &fp, cudaStream_t s
 #define RT_STRICT(CH) launch_kernel(draw_brute_kernel<sfloat, CH>, ctx, fp, stream)
     RT_DISPATCH_CH(RT_STRICT);
   }
+  if (fp.ray_counters) {  // RT_FLAG_COUNT_RAYS: the generic kernel carries the counters
+#define RT_COUNTING(CH) launch_kernel(draw_brute_kernel<float, CH>, ctx, fp, stream)
+    RT_DISPATCH_CH(RT_COUNTING);
+  }
 #define RT_FAST(CH) launch_fast_ch##CH(ctx, fp, stream)
   RT_DISPATCH_CH(RT_FAST);
 }

@@ -36,6 +36,7 @@ struct rt_ctx {
   std::vector<void *> bvh_allocs;   // device allocations owned by the BVH
   int sm_count = 0;
   uint64_t launches = 0;
+  unsigned long long *d_ray_counters = nullptr;  // RT_FLAG_COUNT_RAYS
   size_t launch_extra_smem = 0;
   // launch-order tables keyed by (row0, rows): centre-out order of the 16-row block grid
   struct TileOrder { int row0, rows, tile_h; int *d_order; };

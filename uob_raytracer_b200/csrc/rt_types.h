@@ -21,6 +21,8 @@ struct FrameParams {
   float rot[9];    // rows r0, r1, r2 (skeleton.cpp:149-151)
   float cam[3], light[3];
   uint32_t *out;   // whole-frame ARGB buffer (may be a peer pointer)
+  // RT_FLAG_COUNT_RAYS: {primary, shadow, bounce} rays traced, SURVEY.md §8d definition (else NULL)
+  unsigned long long *ray_counters;
 };
 
 
