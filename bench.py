@@ -256,8 +256,10 @@ def run_ours(args, cfg) -> int:
     # Multi-GPU gather of the frame on rank 0:
     #   nccl: contiguous row tiles, in-place NCCL all-gather into every rank's frame (the north-star path)
     #   p2p : 16x16 blocks interleaved over the ranks (near-perfect balance), every rank's draw kernel
-    #         stores its pixels straight into rank 0's frame over NVLink (CUDA IPC mapping); the only
-    #         collective left is a 4-byte all-reduce that orders rank 0 after the peers' stores
+    #         stores its pixels straight into rank 0's frame over NVLink (CUDA IPC mapping); the hand-over is
+    #         a pair of flags in rank 0's memory (rt_peer_signal / rt_peer_wait: release store after a
+    #         system fence, acquire spin) — no collective at all
+    #   p2p-nccl: the same stores, ordered by a 4-byte NCCL all-reduce instead of the flags
     gather = args.gather if world > 1 else "none"
     if gather == "auto":
         gather = "p2p"
@@ -271,7 +273,8 @@ def run_ours(args, cfg) -> int:
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=f"cuda:{local_rank}")  # > 126 MB L2
     token = torch.zeros(1, dtype=torch.int32, device=f"cuda:{local_rank}")
     peer_ptr = 0
-    if gather == "p2p":
+    fno = [0]  # frame number, the value the hand-over flags count up to
+    if gather in ("p2p", "p2p-nccl"):
         r = u.Renderer(W, H, cfg.aa, cfg.shadow_samples, cfg.max_bounces, device=local_rank, block_stride=world,
                        block_phase=rank)
         handle = [r.ipc_export_frame() if rank == 0 else None]
@@ -284,14 +287,27 @@ def run_ours(args, cfg) -> int:
     r.upload_scene(scene)
     r.set_stream(sptr)
 
+    flags = target + 4 * W * H  # rank 0's hand-over flags: [r] = rank r finished frame f, [32] = rank 0 consumed frame f
+    consumed_flag = flags + 4 * 32
+
     def render_only():
+        fno[0] += 1
+        if gather == "p2p" and rank != 0:
+            r.peer_wait(consumed_flag, 1, fno[0] - 1, sptr)  # rank 0 is done with the previous frame
         r.render_device(rot, cam4, light4, cfg.focal, dev_ptr=target, stream=sptr)
 
-    def gather_only():
+    def gather_only(consume=True):
         if gather == "nccl":
             dist.all_gather_into_tensor(frame, tile)
-        elif gather == "p2p":
+        elif gather == "p2p-nccl":
             dist.all_reduce(token)  # orders rank 0's next use of its frame after every peer's stores
+        elif gather == "p2p":
+            if rank == 0:
+                r.peer_wait(flags + 4, world - 1, fno[0], sptr)
+                if consume:
+                    r.peer_signal(consumed_flag, fno[0], sptr)
+            else:
+                r.peer_signal(flags + 4 * rank, fno[0], sptr)
 
     def step_device():
         render_only()
@@ -303,7 +319,7 @@ def run_ours(args, cfg) -> int:
     step_device()
     torch.cuda.synchronize()
     if rank == 0:
-        if gather == "p2p":
+        if gather in ("p2p", "p2p-nccl"):
             r.read_frame_host_ptr(host.data_ptr())
         else:
             host.copy_(frame)
@@ -362,10 +378,13 @@ def run_ours(args, cfg) -> int:
     else:
         # every rank: render tile -> all-gather -> rank 0 reads the whole frame back
         def step_e2e():
-            step_device()
+            render_only()
+            gather_only(consume=False)
             if rank == 0:
-                if gather == "p2p":
+                if gather in ("p2p", "p2p-nccl"):
                     r.read_frame_host_ptr(host.data_ptr())  # D2H on the same stream, blocking
+                    if gather == "p2p":
+                        r.peer_signal(consumed_flag, fno[0], sptr)  # the peers may overwrite the frame now
                 else:
                     host.copy_(frame, non_blocking=True)
             torch.cuda.synchronize()
@@ -381,7 +400,7 @@ def run_ours(args, cfg) -> int:
         t_e2e = float(t_e2e.cpu())
         e2e_line = {"value": round(counts["rays"] / t_e2e / 1e6, 1), "unit": UNIT, "ms_per_step": round(t_e2e * 1e3, 4),
                     "h2d_bytes_per_step": 84, "d2h_bytes_per_step": W * H * 4,
-                    "api": "rt_render_device per rank + " + ("NCCL all-gather" if gather == "nccl" else "peer stores into rank 0's frame + 4-byte all-reduce") + " + read-back on rank 0"}
+                    "api": "rt_render_device per rank + " + ("NCCL all-gather" if gather == "nccl" else "peer stores into rank 0's frame + " + ("flag hand-over" if gather == "p2p" else "4-byte all-reduce")) + " + read-back on rank 0"}
 
     if rank == 0:
         ms_per_step = total_step_ms / args.steps
@@ -398,7 +417,7 @@ def run_ours(args, cfg) -> int:
                        "shadow_samples": cfg.shadow_samples, "max_bounces": cfg.max_bounces, "focal": cfg.focal,
                        "rays_per_frame": counts["rays"], "rays_source": rays_source, "triangles": scene.n,
                        "partition": (f"{world} row tile(s) of {rows} rows" + (", in-place NCCL all-gather per frame" if world > 1 else ""))
-                       if gather != "p2p" else f"16x16-pixel blocks interleaved over {world} ranks, peer stores into rank 0's frame over NVLink + 4-byte all-reduce per frame",
+                       if gather not in ("p2p", "p2p-nccl") else f"16x16-pixel blocks interleaved over {world} ranks, peer stores into rank 0's frame over NVLink + " + ("release/acquire flag hand-over" if gather == "p2p" else "4-byte all-reduce") + " per frame",
                        "gather": gather,
                        "l2": "flushed between timed iterations (256 MiB memset outside the timed event pairs); "
                              "the scene is 3.4 KB and lives in shared memory",
@@ -449,8 +468,11 @@ def run_ours(args, cfg) -> int:
                           f", best of {i + 1} frames; verbatim kernels.cl via g++ shim (-O2, strict IEEE), all host threads",
                 "ms_per_frame": None if mesh else round(best * step * 1e3, 1)}
         print(json.dumps(line), flush=True)
+    torch.cuda.synchronize()
+    r.synchronize()  # surfaces a timed-out rt_peer_wait
+    if dist is not None:
+        dist.barrier()
     if peer_ptr:
-        torch.cuda.synchronize()
         r.ipc_close_frame(peer_ptr)
     if dist is not None:
         dist.barrier()
@@ -469,7 +491,7 @@ def main() -> int:
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
     ap.add_argument("--workload", default="cfg2")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--gather", choices=["auto", "nccl", "p2p"], default="auto",
+    ap.add_argument("--gather", choices=["auto", "nccl", "p2p", "p2p-nccl"], default="auto",
                     help="N>1: how the frame reaches rank 0 (auto = p2p)")
     args = ap.parse_args()
     import uob_raytracer_b200 as u

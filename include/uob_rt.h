@@ -157,6 +157,19 @@ int rt_ipc_export_frame(rt_ctx *ctx, void *handle64);
 int rt_ipc_open_frame(rt_ctx *ctx, const void *handle64, uint32_t **dev_argb);
 int rt_ipc_close_frame(rt_ctx *ctx, uint32_t *dev_argb);
 
+/* Frame hand-over between GPUs without a collective.  Every frame buffer carries RT_PEER_FLAGS 32-bit
+ * flags behind its pixels (rt_peer_flags() of the owner; at dev_argb + width*height through a mapping).
+ * rt_peer_signal enqueues "all my earlier work on this stream is visible system-wide, then flag = value";
+ * rt_peer_wait enqueues "wait until each of the n flags is >= value" (a one-warp kernel spinning with
+ * system-scope loads; gives up after ~2 s and records an error readable with rt_last_error after
+ * rt_synchronize).  Typical frame f:  peers: wait(owner's consumed flag >= f-1), draw into the owner's
+ * frame, signal(done[rank] = f);  owner: draw, wait(done[1..N-1] >= f), read back, signal(consumed = f).
+ * Only between DIFFERENT GPUs: a waiting kernel and the kernel it waits for must not share a device. */
+#define RT_PEER_FLAGS 64
+uint32_t *rt_peer_flags(rt_ctx *ctx);
+int rt_peer_signal(rt_ctx *ctx, uint32_t *dev_flag, uint32_t value, void *stream);
+int rt_peer_wait(rt_ctx *ctx, const uint32_t *dev_flags, int n, uint32_t value, void *stream);
+
 /* Blocking read-back of the WHOLE frame buffer of this context (width*height uint32) — what the
  * owner of a peer-written frame calls once the peers are done. */
 int rt_read_frame(rt_ctx *ctx, uint32_t *host_argb);

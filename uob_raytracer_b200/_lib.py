@@ -56,6 +56,9 @@ RT_SYMBOLS = {
     "rt_ipc_export_frame": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p]),
     "rt_ipc_open_frame": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.POINTER(ctypes.c_void_p)]),
     "rt_ipc_close_frame": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p]),
+    "rt_peer_flags": (ctypes.c_void_p, [ctypes.c_void_p]),
+    "rt_peer_signal": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_uint32, ctypes.c_void_p]),
+    "rt_peer_wait": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_uint32, ctypes.c_void_p]),
     "rt_read_frame": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p]),
     "rt_version": (ctypes.c_char_p, []),
 }

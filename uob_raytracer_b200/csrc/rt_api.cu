@@ -87,6 +87,7 @@ static int free_ctx(rt_ctx *ctx) {
   if (ctx->d_frame) cudaFree(ctx->d_frame);
   if (ctx->d_scene) cudaFree(ctx->d_scene);
   if (ctx->d_ray_counters) cudaFree(ctx->d_ray_counters);
+  if (ctx->d_wait_status) cudaFree(ctx->d_wait_status);
   for (auto &t : ctx->tile_orders) cudaFree(t.d_order);
   rt::bvh_free(ctx);
   for (int b = 0; b < rt_ctx::kBands; b++) {
@@ -160,14 +161,17 @@ rt_ctx *rt_create(const rt_config *cfg) {
     if ((e = cudaEventCreateWithFlags(&ctx->band_done[b], cudaEventDisableTiming)) != cudaSuccess) return fail("creating event", e);
   }
   if ((e = cudaEventCreateWithFlags(&ctx->band_start, cudaEventDisableTiming)) != cudaSuccess) return fail("creating event", e);
-  if ((e = cudaMalloc(&ctx->d_frame, sizeof(uint32_t) * (size_t)cfg->width * cfg->height)) != cudaSuccess)
-    return fail("creating screen buffer", e);
+  // the frame, followed by RT_PEER_FLAGS hand-over flags (same allocation, so one IPC handle maps both)
+  const size_t frame_words = (size_t)cfg->width * cfg->height + RT_PEER_FLAGS;
+  if ((e = cudaMalloc(&ctx->d_frame, sizeof(uint32_t) * frame_words)) != cudaSuccess) return fail("creating screen buffer", e);
+  if ((e = cudaMalloc(&ctx->d_wait_status, sizeof(int))) != cudaSuccess) return fail("creating wait status", e);
+  if ((e = cudaMemsetAsync(ctx->d_wait_status, 0, sizeof(int), ctx->stream)) != cudaSuccess) return fail("clearing wait status", e);
   if (cfg->flags & RT_FLAG_COUNT_RAYS) {
     if ((e = cudaMalloc(&ctx->d_ray_counters, 3 * sizeof(unsigned long long))) != cudaSuccess) return fail("creating ray counters", e);
     if ((e = cudaMemsetAsync(ctx->d_ray_counters, 0, 3 * sizeof(unsigned long long), ctx->stream)) != cudaSuccess)
       return fail("clearing ray counters", e);
   }
-  if ((e = cudaMemsetAsync(ctx->d_frame, 0, sizeof(uint32_t) * (size_t)cfg->width * cfg->height, ctx->stream)) != cudaSuccess)
+  if ((e = cudaMemsetAsync(ctx->d_frame, 0, sizeof(uint32_t) * frame_words, ctx->stream)) != cudaSuccess)
     return fail("clearing screen buffer", e);
   return ctx;
 }
@@ -424,6 +428,34 @@ int rt_synchronize(rt_ctx *ctx) {
   if (!ctx) return RT_ERR_INVALID;
   RT_CUDA(ctx, cudaSetDevice(ctx->cfg.device), "selecting device");
   RT_CUDA(ctx, cudaStreamSynchronize(ctx->stream), "waiting for the stream");
+  if (ctx->peer_waits) {  // did a rt_peer_wait give up?
+    int status = 0;
+    RT_CUDA(ctx, cudaMemcpy(&status, ctx->d_wait_status, sizeof status, cudaMemcpyDeviceToHost), "reading wait status");
+    if (status) {
+      ctx->err = "rt_peer_wait: timed out waiting for a peer GPU's flag";
+      return RT_ERR_CUDA;
+    }
+  }
+  return RT_OK;
+}
+
+uint32_t *rt_peer_flags(rt_ctx *ctx) { return ctx ? ctx->d_frame + (size_t)ctx->cfg.width * ctx->cfg.height : nullptr; }
+
+int rt_peer_signal(rt_ctx *ctx, uint32_t *dev_flag, uint32_t value, void *stream) {
+  if (!ctx || !dev_flag) return RT_ERR_INVALID;
+  RT_CUDA(ctx, cudaSetDevice(ctx->cfg.device), "selecting device");
+  RT_CUDA(ctx, rt::launch_peer_signal(dev_flag, value, stream ? (cudaStream_t)stream : ctx->stream), "enqueueing peer signal");
+  ctx->launches++;
+  return RT_OK;
+}
+
+int rt_peer_wait(rt_ctx *ctx, const uint32_t *dev_flags, int n, uint32_t value, void *stream) {
+  if (!ctx || !dev_flags || n < 1 || n > 32) return RT_ERR_INVALID;
+  RT_CUDA(ctx, cudaSetDevice(ctx->cfg.device), "selecting device");
+  RT_CUDA(ctx, rt::launch_peer_wait(dev_flags, n, value, ctx->d_wait_status, stream ? (cudaStream_t)stream : ctx->stream),
+          "enqueueing peer wait");
+  ctx->launches++;
+  ctx->peer_waits = true;
   return RT_OK;
 }
 

@@ -37,6 +37,8 @@ struct rt_ctx {
   int sm_count = 0;
   uint64_t launches = 0;
   unsigned long long *d_ray_counters = nullptr;  // RT_FLAG_COUNT_RAYS
+  int *d_wait_status = nullptr;                  // set by a rt_peer_wait kernel that timed out
+  bool peer_waits = false;
   size_t launch_extra_smem = 0;
   // launch-order tables keyed by (row0, rows): centre-out order of the 16-row block grid
   struct TileOrder { int row0, rows, tile_h; int *d_order; };
@@ -50,6 +52,9 @@ namespace rt {
 cudaError_t launch_draw_brute(rt_ctx *ctx, const FrameParams &fp, cudaStream_t stream);
 size_t brute_smem_bytes(int n, int n_sh);
 size_t brute_smem_limit();
+// rt_peak.cu (small utility kernels)
+cudaError_t launch_peer_signal(uint32_t *flag, uint32_t value, cudaStream_t stream);
+cudaError_t launch_peer_wait(const uint32_t *flags, int n, uint32_t value, int *status, cudaStream_t stream);
 // rt_bvh.cu
 cudaError_t bvh_build(rt_ctx *ctx, const float *verts, const float *normals, const float *colors, int n);
 void bvh_free(rt_ctx *ctx);

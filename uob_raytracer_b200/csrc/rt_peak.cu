@@ -1,4 +1,4 @@
-// rt_peak.cu — FP32 (non-tensor) pipe microbenchmark: the roofline denominator of the
+// rt_peak.cu — small utility kernels: the FP32 (non-tensor) pipe microbenchmark: the roofline denominator of the
 // brute-force render path.  MEASURED_PEAKS.json carries HBM and bf16-tensor peaks only, and
 // this path is neither, so the FFMA peak is measured in the same run, on the
 // same clocks, as the kernel it bounds.
@@ -20,6 +20,42 @@ __global__ void __launch_bounds__(256) ffma_peak_kernel(float *out, int iters, f
 #pragma unroll
   for (int k = 0; k < kIlp; k++) s += acc[k];
   if (s == 123.456f) out[0] = s;  // never true; keeps the chain alive
+}
+
+// ---- frame hand-over flags between GPUs (include/uob_rt.h: rt_peer_signal / rt_peer_wait) ----
+
+__global__ void peer_signal_kernel(uint32_t *flag, uint32_t value) {
+  // Everything this stream did before (the draw kernel's stores into the peer's frame) happened-before this
+  // kernel; the system-scope fence makes it visible to the other GPU before the flag is.
+  __threadfence_system();
+  asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(flag), "r"(value) : "memory");
+}
+
+__global__ void peer_wait_kernel(const uint32_t *flags, int n, uint32_t value, int *status) {
+  if ((int)threadIdx.x >= n) return;
+  const uint32_t *f = flags + threadIdx.x;
+  const long long t0 = clock64();
+  for (;;) {
+    uint32_t v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(f) : "memory");
+    if ((int32_t)(v - value) >= 0) break;
+    if (clock64() - t0 > 4000000000ll) {  // ~2 s at 2 GHz: give up instead of hanging the GPU
+      atomicExch(status, 1);
+      break;
+    }
+    __nanosleep(200);
+  }
+  __threadfence_system();
+}
+
+cudaError_t launch_peer_signal(uint32_t *flag, uint32_t value, cudaStream_t stream) {
+  peer_signal_kernel<<<1, 1, 0, stream>>>(flag, value);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_peer_wait(const uint32_t *flags, int n, uint32_t value, int *status, cudaStream_t stream) {
+  peer_wait_kernel<<<1, 32, 0, stream>>>(flags, n, value, status);
+  return cudaGetLastError();
 }
 
 }  // namespace rt

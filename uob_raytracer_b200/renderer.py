@@ -131,6 +131,20 @@ class Renderer:
     def ipc_close_frame(self, dev_ptr: int) -> None:
         self._check(self._lib.rt_ipc_close_frame(self._ctx, dev_ptr))
 
+    # -- frame hand-over flags between GPUs ------------------------------------
+    PEER_FLAGS = 64
+
+    @property
+    def peer_flags_ptr(self) -> int:
+        """Device address of this context's hand-over flags (behind the pixels of its frame buffer)."""
+        return int(self._lib.rt_peer_flags(self._ctx) or 0)
+
+    def peer_signal(self, flag_ptr: int, value: int, stream: int = 0) -> None:
+        self._check(self._lib.rt_peer_signal(self._ctx, flag_ptr, value, stream or None))
+
+    def peer_wait(self, flags_ptr: int, n: int, value: int, stream: int = 0) -> None:
+        self._check(self._lib.rt_peer_wait(self._ctx, flags_ptr, n, value, stream or None))
+
     def set_stream(self, stream: int) -> None:
         """Use the caller's cudaStream_t (0 = back to the context's own) for everything that follows."""
         self._check(self._lib.rt_set_stream(self._ctx, stream or None))
