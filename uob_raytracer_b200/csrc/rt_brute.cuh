@@ -73,15 +73,19 @@ template <class T> struct ClosestState {
   }
 };
 
-// One ray/triangle test of the closest-hit search (kernels.cl:102-128).  `ordered`: the caller
-// visits triangles in ascending index, so `t < current` alone implements the tie rule.
-template <class T, bool ORDERED>
+// One ray/triangle test of the closest-hit search (kernels.cl:102-128).  ORDERED: the caller visits
+// triangles in ascending index, so `t < current` alone implements the tie rule.  PRECISE: the fast
+// policy also uses the reference's cofactor expressions (with FMA) instead of the cheaper triple
+// products — for the sub-pixel triangles of a mesh, where u and v are differences of nearly equal
+// numbers and the cheaper form misplaces visibly more edge hits (measured: 21 vs 5 pixels of a 96x96
+// frame over a 5,120-triangle mesh).
+template <class T, bool ORDERED, bool PRECISE = false>
 __device__ __forceinline__ void closest_tri_test(float4 A, float4 Bq, float4 C, V3<T> start, V3<T> nd, int id, int slot,
                                                  ClosestState<T> &cs) {
   const V3<T> v0 = xyz<T>(A), e1 = xyz<T>(Bq), e2 = xyz<T>(C);
   const T c0 = T(A.w), c1 = T(Bq.w), c2 = T(C.w);
   const V3<T> b = start - v0;
-  if constexpr (is_strict<T>::value) {
+  if constexpr (is_strict<T>::value || PRECISE) {
     const T detA = (nd.x * c0 - nd.y * c1) + nd.z * c2;
     const T inv = rcp_(detA);
     const T t = ((b.x * c0 - b.y * c1) + b.z * c2) * inv;
@@ -216,6 +220,50 @@ __device__ __forceinline__ void shadow_pair(float4 A, float4 Bq, float4 C, V3<T>
   }
 }
 
+// jitter components lie in [-0.025, 0.025] (crush, kernels.cl:49-52): |j| <= 0.025*sqrt(3) = 0.0433013
+constexpr float kJitterMax = 0.0445f;  // inflated by 2.7 %
+constexpr float kSlack = 1.002f;
+
+__device__ __forceinline__ float xor_sign(float v, unsigned signbit) { return __uint_as_float(__float_as_uint(v) ^ signbit); }
+
+// Fast-policy (origin, triangle) pair with the two conservative culls of rt_fast.cuh (plane, edges) in front of
+// the division-free per-sample test, for callers that hold the CH ray directions in registers.
+// bound = (jmax|N|, jmax|e1|, jmax|e2|, -); r = un-jittered direction; kk >= |r|/|d_k| for every k; inv_r2 = 1/|r|^2.
+template <int CH>
+__device__ __forceinline__ void shadow_pair_culled(float4 A, float4 Bq, float4 C, float4 bound, V3<float> start, V3<float> r,
+                                                   const ShadowRays<float, CH> &rays, float kk, float inv_r2, unsigned &occ,
+                                                   unsigned alive = 0xffffffffu) {
+  const V3<float> b(start.x - A.x, start.y - A.y, start.z - A.z);
+  const float c0 = A.w, c1 = Bq.w, c2 = C.w;
+  const float num = (b.x * c0 - b.y * c1) + b.z * c2;  // det[b,e1,e2] = b.N
+  const float rN = (r.x * c0 - r.y * c1) + r.z * c2;
+  const float w = xor_sign(rN, __float_as_uint(num) & 0x80000000u);
+  if (fabsf(num) >= (bound.x - w) * kk) return;  // plane cull: no sample passes stage 1
+  const V3<float> e1(Bq.x, Bq.y, Bq.z), e2(C.x, C.y, C.z);
+  const V3<float> U(b.y * e2.z - b.z * e2.y, b.z * e2.x - b.x * e2.z, b.x * e2.y - b.y * e2.x);  // b x e2
+  const V3<float> V(e1.y * b.z - e1.z * b.y, e1.z * b.x - e1.x * b.z, e1.x * b.y - e1.y * b.x);  // e1 x b
+  const float arN = fabsf(rN);
+  if (arN > bound.x) {  // every sample has sign(dn) = sign(rN): edge cull on the un-jittered ray
+    const float lb = sqrt_approx(dot(b, b));
+    const float mU = lb * bound.z, mV = lb * bound.y;
+    const unsigned sg = __float_as_uint(rN) & 0x80000000u;
+    const float eu = xor_sign(dot(r, U), sg), ev = xor_sign(dot(r, V), sg);
+    if ((eu < -mU) | (ev < -mV) | ((eu + ev) - (mU + mV) > arN + bound.x)) return;
+  }
+  const float q1 = num * num * inv_r2;  // t^2 |d|^2 < r^2  <=>  q1 |d|^2 < dn^2
+  const unsigned numb = __float_as_uint(num);
+#pragma unroll
+  for (int k = 0; k < CH; k++) {
+    const V3<float> d = rays.d[k];
+    const float dn = (d.x * c0 - d.y * c1) + d.z * c2;  // det A = -dn; t = -num/dn; u = E1/dn; v = E2/dn
+    const float E1 = dot(d, U), E2 = dot(d, V);
+    const unsigned dnb = __float_as_uint(dn);
+    const unsigned sx = ((__float_as_uint(E1) ^ dnb) | (__float_as_uint(E2) ^ dnb)) | ~(numb ^ dnb);
+    const bool hit = ((int)sx >= 0) & (fabsf(E1 + E2) <= fabsf(dn)) & (q1 * rays.dd[k] < dn * dn) & (((alive >> k) & 1u) != 0u);
+    occ |= hit ? (1u << k) : 0u;
+  }
+}
+
 // Sphere part of in_shadow (kernels.cl:278-307)
 template <class T, int CH>
 __device__ __forceinline__ void shadow_spheres(V3<T> start, const ShadowRays<T, CH> &rays, T radius_sq, unsigned &occ) {
@@ -262,6 +310,11 @@ __device__ __forceinline__ void shadow_spheres(V3<T> start, const ShadowRays<T, 
 // ---------------------------------------------------------------------------
 template <class T> struct BruteTracer {
   SceneView sc;
+  __device__ __forceinline__ BruteTracer<sfloat> strict() const {  // same scene, reference arithmetic
+    BruteTracer<sfloat> t;
+    t.sc = sc;
+    return t;
+  }
 
   __device__ __forceinline__ void closest(V3<T> start, V3<T> dir, HitRec<T> &hit) const {
     ClosestState<T> cs;
@@ -403,12 +456,36 @@ __device__ __forceinline__ uint32_t shade_pixel(const Tracer &tr, const FramePar
   for (int dy = 0; dy < A; dy++) {
 #pragma unroll 1
     for (int dx = 0; dx < A; dx++) {
-      const V3<T> d0 = base + V3<T>(T(__int2float_rn(dx)), T(__int2float_rn(dy)), T(0.0f));
-      V3<T> dir = normalize(V3<T>(dot(r0, d0), dot(r1, d0), dot(r2, d0)));
+      V3<T> dir;
       HitRec<T> hit;
       hit.id = -1;
       hit.color = make_float4(0.0f, 0.0f, 0.0f, 1.0f);
-      tr.closest(cam, dir, hit);
+      if constexpr (is_strict<T>::value) {
+        const V3<T> d0 = base + V3<T>(T(__int2float_rn(dx)), T(__int2float_rn(dy)), T(0.0f));
+        dir = normalize(V3<T>(dot(r0, d0), dot(r1, d0), dot(r2, d0)));
+        tr.closest(cam, dir, hit);
+      } else {
+        // Fast policy: the PRIMARY ray and its hit are still evaluated with the reference's exact sequence
+        // (a small part of the work), so that primary visibility is bit-identical to the reference — the
+        // default camera puts box edges exactly on pixel boundaries.
+        typedef sfloat S;
+        const S SWs(__int2float_rn(p.W)), SHs(__int2float_rn(p.H)), fAs(__int2float_rn(A));
+        const V3<S> bs(S(__int2float_rn(x * A)) - div_(SWs * fAs, S(2.0f)), S(__int2float_rn(y * A)) - div_(SHs * fAs, S(2.0f)), S(p.focal));
+        const V3<S> d0 = bs + V3<S>(S(__int2float_rn(dx)), S(__int2float_rn(dy)), S(0.0f));
+        const V3<S> s0(S(p.rot[0]), S(p.rot[1]), S(p.rot[2])), s1(S(p.rot[3]), S(p.rot[4]), S(p.rot[5])), s2(S(p.rot[6]), S(p.rot[7]), S(p.rot[8]));
+        const V3<S> ds = normalize(V3<S>(dot(s0, d0), dot(s1, d0), dot(s2, d0)));
+        HitRec<S> hs;
+        hs.id = -1;
+        hs.color = hit.color;
+        hs.point = V3<S>(S(0.0f), S(0.0f), S(0.0f));
+        hs.normal = hs.point;
+        tr.strict().closest(V3<S>(S(p.cam[0]), S(p.cam[1]), S(p.cam[2])), ds, hs);
+        dir = V3<T>(ds.x.v, ds.y.v, ds.z.v);
+        hit.id = hs.id;
+        hit.point = V3<T>(hs.point.x.v, hs.point.y.v, hs.point.z.v);
+        hit.normal = V3<T>(hs.normal.x.v, hs.normal.y.v, hs.normal.z.v);
+        hit.color = hs.color;
+      }
       float medium = RT_AIR;
       bool bounced = false;
       int bounce = 0;

@@ -77,6 +77,16 @@ __global__ void bvh_gather_kernel(const float4 *__restrict__ verts, const float4
   leaf_hi[s] = make_float4(fmaxf(v0.x, fmaxf(v1.x, v2.x)), fmaxf(v0.y, fmaxf(v1.y, v2.y)), fmaxf(v0.z, fmaxf(v1.z, v2.z)), 0.0f);
 }
 
+// Bounds used by the fast policy's per-(point, triangle) culls for the triangles kept out of the tree.
+__global__ void bvh_big_bounds_kernel(const float4 *__restrict__ tri_a, const float4 *__restrict__ tri_b, const float4 *__restrict__ tri_c,
+                                      int n_bvh, int n, float4 *__restrict__ out) {
+  const int s = n_bvh + blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= n) return;
+  const float4 A = tri_a[s], B = tri_b[s], C = tri_c[s];
+  out[s - n_bvh] = make_float4(kJitterMax * sqrtf(A.w * A.w + B.w * B.w + C.w * C.w), kJitterMax * sqrtf(B.x * B.x + B.y * B.y + B.z * B.z),
+                               kJitterMax * sqrtf(C.x * C.x + C.y * C.y + C.z * C.z), 0.0f);
+}
+
 __device__ __forceinline__ int key_delta(const unsigned long long *keys, int n, int i, int j) {
   if (j < 0 || j >= n) return -1;
   return __clzll((long long)(keys[i] ^ keys[j]));
@@ -351,8 +361,15 @@ cudaError_t bvh_build(rt_ctx *ctx, const float *verts, const float *normals, con
     bvh_emit_kernel<<<b2, tpb, 0, st>>>(n_bvh, left, right, first, last, leaf_lo, leaf_hi, node_lo, node_hi, pad, nodes);
     BVH_TRY(cudaGetLastError());
   }
+  float4 *big_bound = nullptr;
+  BVH_TRY(dev_alloc(ctx, &big_bound, (size_t)(n - n_bvh), true));
+  if (n > n_bvh) {
+    bvh_big_bounds_kernel<<<(n - n_bvh + tpb - 1) / tpb, tpb, 0, st>>>(tri_a, tri_b, tri_c, n_bvh, n, big_bound);
+    BVH_TRY(cudaGetLastError());
+  }
   BVH_TRY(cudaStreamSynchronize(st));
   cleanup();
+  bv->big_bound = big_bound;
   bv->tri_a = tri_a;
   bv->tri_b = tri_b;
   bv->tri_c = tri_c;

@@ -26,12 +26,12 @@ namespace rt {
 
 constexpr int kBvhLeafMax = 4;       // triangles per leaf (<= 8 by the ref encoding)
 constexpr int kBvhStack = 64;
-constexpr float kBvhJitterMax = 0.0445f;  // same inflated bound as the fast brute-force path
 
 struct BvhView {
   const float4 *tri_a, *tri_b, *tri_c, *tri_n, *tri_col;
   const int *tri_id;
   const float4 *nodes;
+  const float4 *big_bound;  // per big triangle (slot - n_bvh): (jmax|N|, jmax|e1|, jmax|e2|, -) for the fast policy's culls
   int n, n_bvh;      // all triangles / those covered by the tree
   int root;          // root reference (may be a leaf)
   int all_casters;   // no triangle has material -1
@@ -55,6 +55,11 @@ __device__ __forceinline__ float box_entry(float lox, float loy, float loz, floa
 
 template <class T> struct BvhTracer {
   BvhView bv;
+  __device__ __forceinline__ BvhTracer<sfloat> strict() const {  // same tree, reference arithmetic
+    BvhTracer<sfloat> t;
+    t.bv = bv;
+    return t;
+  }
 
   // kernels.cl:92-166 / :168-241
   __device__ void closest(V3<T> start, V3<T> dir, HitRec<T> &hit) const {
@@ -96,7 +101,7 @@ template <class T> struct BvhTracer {
           const int first = (~ref) >> 3, cnt = ((~ref) & 7) + 1;
           for (int k = 0; k < cnt; k++) {
             const int s = first + k;
-            closest_tri_test<T, false>(__ldg(bv.tri_a + s), __ldg(bv.tri_b + s), __ldg(bv.tri_c + s), start, nd, __ldg(bv.tri_id + s), s, cs);
+            closest_tri_test<T, false, true>(__ldg(bv.tri_a + s), __ldg(bv.tri_b + s), __ldg(bv.tri_c + s), start, nd, __ldg(bv.tri_id + s), s, cs);
           }
         }
         if (sp == 0) break;
@@ -120,10 +125,21 @@ template <class T> struct BvhTracer {
   __device__ unsigned shadow(V3<T> start, const ShadowRays<T, CH> &rays, V3<T> r, T radius_sq) const {
     constexpr unsigned FULL = (CH >= 32) ? 0xffffffffu : ((1u << CH) - 1u);
     unsigned occ = 0u;
-    for (int s = bv.n_bvh; s < bv.n; s++) {
-      if (!casts_shadow(s)) continue;
-      shadow_pair<T, CH>(bv.tri_a[s], bv.tri_b[s], bv.tri_c[s], start, rays, radius_sq, occ);
-      if (occ == FULL) return occ;
+    if constexpr (is_strict<T>::value) {
+      for (int s = bv.n_bvh; s < bv.n; s++) {
+        if (!casts_shadow(s)) continue;
+        shadow_pair<T, CH>(bv.tri_a[s], bv.tri_b[s], bv.tri_c[s], start, rays, radius_sq, occ);
+        if (occ == FULL) return occ;
+      }
+    } else {
+      // the big triangles are the room: almost all of them are culled per shading point (rt_fast.cuh)
+      const float Rb = sqrt_approx(radius_sq), inv_r2 = rcp_approx(radius_sq);
+      const float kk = (Rb > 2.0f * kJitterMax) ? kSlack * Rb * rcp_approx(Rb - kJitterMax) : 1e30f;
+      for (int s = bv.n_bvh; s < bv.n; s++) {
+        if (!casts_shadow(s)) continue;
+        shadow_pair_culled<CH>(bv.tri_a[s], bv.tri_b[s], bv.tri_c[s], bv.big_bound[s - bv.n_bvh], start, r, rays, kk, inv_r2, occ);
+        if (occ == FULL) return occ;
+      }
     }
     if (bv.n_bvh > 0) {
       // Packet traversal: the CH rays share every node fetch; each node is tested against every ray

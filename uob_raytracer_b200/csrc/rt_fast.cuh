@@ -41,9 +41,7 @@
 
 namespace rt {
 
-// jitter components lie in [-0.025, 0.025] (crush, kernels.cl:49-52): |j| <= 0.025*sqrt(3) = 0.0433013
-constexpr float kJitterMax = 0.0445f;  // inflated by 2.7 %
-constexpr float kSlack = 1.002f;
+// kJitterMax / kSlack (the inflated bound on |j| and the slack factor) live in rt_brute.cuh.
 
 // Shared-memory view of the fast kernel.
 //   prim[3i+0] = (c0, c1, c2, det[b,e1,e2])     b = cam - v0
@@ -102,8 +100,6 @@ __device__ __forceinline__ bool box_may_be_shadowed_by(const float4 *shad, int c
   }
   return true;
 }
-
-__device__ __forceinline__ float xor_sign(float v, unsigned signbit) { return __uint_as_float(__float_as_uint(v) ^ signbit); }
 
 // Per-triangle constants of rays starting at `cam`, with the reference's (strict) operation
 // sequence, so the confirm step reproduces the reference's decisions bit for bit.
