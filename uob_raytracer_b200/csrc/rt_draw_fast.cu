@@ -51,7 +51,8 @@ __global__ void __launch_bounds__(kThreads, RT_MINBLOCKS) draw_fast_kernel(const
   __syncthreads();
 
   // ---- per-triangle camera constants + binning of the triangles against this block's tile ----
-  {
+  const bool small_scene = n <= 32;  // one warp bins a small scene on its own: no block-wide hand-shakes
+  if (!small_scene || threadIdx.x < 32) {
     // corner rays of the tile in virtual (sub-pixel) coordinates, un-normalised (kernels.cl:384-400)
     const float vx0 = (float)(tile_x * A) - SW * fA * 0.5f;
     const float vy0 = (float)(tile_y * A) - SH * fA * 0.5f;
@@ -94,6 +95,16 @@ __global__ void __launch_bounds__(kThreads, RT_MINBLOCKS) draw_fast_kernel(const
       s_spheres_visible = vis;
     }
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (small_scene) {
+      bool keep = false;
+      if (lane < n) {
+        primary_constants(sc.g, prim, cam, lane);
+        keep = tile_may_hit(prim, lane, dc, dmax);
+      }
+      const unsigned ballot = __ballot_sync(0xffffffffu, keep);
+      if (keep) plist[__popc(ballot & ((1u << lane) - 1u))] = lane;
+      if (lane == 0) s_base = __popc(ballot);
+    } else
     for (int base = 0; base < n; base += kThreads) {
       const int i = base + threadIdx.x;
       bool keep = false;
@@ -115,9 +126,9 @@ __global__ void __launch_bounds__(kThreads, RT_MINBLOCKS) draw_fast_kernel(const
       __syncthreads();
       if (threadIdx.x == 0) s_base += total;
     }
-    __syncthreads();
-    sc.n_prim = s_base;
   }
+  __syncthreads();
+  sc.n_prim = s_base;
   const bool spheres_visible = s_spheres_visible != 0;
 
   const unsigned warp_mask = __ballot_sync(0xffffffffu, in_frame);  // lanes that stay for the warp collectives below
