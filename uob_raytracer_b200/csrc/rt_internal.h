@@ -20,7 +20,10 @@ struct rt_ctx {
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   // rt_render overlaps the read-back with the kernel: the tile is rendered in kBands row bands on
   // their own streams and each band is copied to the host as soon as it is done
-  static constexpr int kBands = 4;
+  #ifndef RT_BANDS
+#define RT_BANDS 4
+#endif
+  static constexpr int kBands = RT_BANDS;
   cudaStream_t band_stream[kBands] = {};
   cudaEvent_t band_done[kBands] = {};
   cudaEvent_t band_start = nullptr;
