@@ -163,3 +163,17 @@ def test_icosphere_generator(tmp_path):
     a = p.read_bytes()
     u.write_icosphere_obj(str(p), 3, 0.2, 0.05)
     assert a == p.read_bytes(), "generator must be deterministic"
+
+
+def test_parallel_obj_ingest_matches_reference_loader(ob, tmp_path):
+    """A mesh big enough for the multi-threaded parser (81,920 faces, > 1 MB of text) against the reference's
+    own load_obj compiled from Loader.cpp: identical bytes."""
+    if not ob.ref_available():
+        pytest.skip("oracle/_ref not built")
+    p = tmp_path / "ico6.obj"
+    assert u.write_icosphere_obj(str(p), 6, 0.2, 0.05) == 81920
+    assert p.stat().st_size > (1 << 20)
+    s = u.load_obj(str(p))
+    v, n, c = ob.ref_load_obj(str(p))
+    assert s.n == 81920 == c.shape[0]
+    assert s.verts.tobytes() == v.tobytes() and s.normals.tobytes() == n.tobytes() and s.colors.tobytes() == c.tobytes()

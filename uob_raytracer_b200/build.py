@@ -14,7 +14,7 @@ CSRC = os.path.join(PKG, "csrc")
 LIB = os.environ.get("UOB_RT_LIB") or os.path.join(PKG, "libuob_rt.so")
 HOST_LIB = os.path.join(PKG, "libuob_host.so")
 HOST_SOURCES = [os.path.join("host", "uob_host.cpp")]
-HOST_FLAGS = ["-std=c++17", "-O2", "-ffp-contract=off", "-fno-fast-math", "-fPIC", "-shared", "-Wall"]
+HOST_FLAGS = ["-std=c++17", "-O2", "-ffp-contract=off", "-fno-fast-math", "-fPIC", "-shared", "-Wall", "-pthread"]
 
 SOURCES = ["rt_api.cu", "rt_draw.cu", "rt_peak.cu", "rt_bvh.cu"]
 NVCC_FLAGS = [

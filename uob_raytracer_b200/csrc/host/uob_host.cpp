@@ -10,7 +10,9 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <functional>
 #include <string>
+#include <thread>
 #include <unordered_map>
 #include <vector>
 
@@ -122,11 +124,45 @@ int flatten(const std::vector<Tri> &tris, float *verts, float *normals, float *c
   return (int)n;
 }
 
-// Minimal OBJ reader with load_obj's semantics (Loader.cpp:27-56).  The
-// reference tokenises each line with operator>>; a line whose first token is
-// exactly "v" or "f" is used, everything else is skipped.  strtof/strtol give
-// the same correctly-rounded values as the stream extractors for well-formed
-// numbers.
+// OBJ reader with load_obj's semantics (Loader.cpp:27-56), built for meshes of a million faces.
+// The reference tokenises each line with operator>>; a line whose first token is exactly "v" or
+// "f" is used, everything else is skipped.  strtof/strtol give the same correctly-rounded values as
+// the stream extractors for well-formed numbers.  The file is read once, cut into one chunk per
+// hardware thread at line boundaries, and every chunk is tokenised in parallel into its own vertex
+// and face lists; face indices are global (1-based over the whole file, as in the reference, which
+// also requires a vertex to precede the faces that use it), so triangles are built in a second
+// parallel pass once all vertices are known.
+struct ObjChunk {
+  std::vector<Vec4> vertices;
+  std::vector<long> faces;  // 3 per face
+  bool bad_face = false;
+};
+
+void parse_chunk(const char *p, const char *end, ObjChunk &out) {
+  while (p < end) {
+    const char *eol = (const char *)memchr(p, '\n', (size_t)(end - p));
+    if (!eol) eol = end;
+    const char *q = p;
+    while (q < eol && (*q == ' ' || *q == '\t' || *q == '\r')) q++;
+    const char *tok = q;
+    while (q < eol && !(*q == ' ' || *q == '\t' || *q == '\r')) q++;
+    if (q - tok == 1 && *tok == 'v') {
+      char *e;
+      const float x = strtof(q, &e);
+      const float y = strtof(e, &e);
+      const float z = strtof(e, &e);
+      out.vertices.push_back(Vec4{1.5f * x, 1.5f * y, 1.5f * z, 1.f});  // Loader.cpp:41
+    } else if (q - tok == 1 && *tok == 'f') {
+      char *e;
+      const long a = strtol(q, &e, 10), b = strtol(e, &e, 10), c = strtol(e, &e, 10);
+      out.faces.push_back(a);
+      out.faces.push_back(b);
+      out.faces.push_back(c);
+    }
+    p = eol + 1;
+  }
+}
+
 bool parse_obj(const char *path, std::vector<Tri> &tris) {
   FILE *f = fopen(path, "rb");
   if (!f) return false;
@@ -139,42 +175,71 @@ bool parse_obj(const char *path, std::vector<Tri> &tris) {
     return false;
   }
   fclose(f);
-  std::vector<Vec4> vertices;
-  const Vec4 blue{0.0f, 0.2f, 0.4f, 0.5f};       // Loader.cpp:20
+  const char *base = buf.c_str(), *end = base + buf.size();
+  unsigned nt = std::thread::hardware_concurrency();
+  if (nt < 1) nt = 1;
+  if (nt > 64) nt = 64;
+  if (buf.size() < (1u << 20)) nt = 1;
+  // chunk boundaries at line starts
+  std::vector<const char *> cut(nt + 1, end);
+  cut[0] = base;
+  for (unsigned t = 1; t < nt; t++) {
+    const char *p = base + buf.size() / nt * t;
+    const char *nl = (const char *)memchr(p, '\n', (size_t)(end - p));
+    cut[t] = nl ? nl + 1 : end;
+  }
+  std::vector<ObjChunk> chunks(nt);
+  {
+    std::vector<std::thread> pool;
+    for (unsigned t = 1; t < nt; t++) pool.emplace_back(parse_chunk, cut[t], cut[t + 1], std::ref(chunks[t]));
+    parse_chunk(cut[0], cut[1], chunks[0]);
+    for (auto &th : pool) th.join();
+  }
+  // vertices of the whole file, and for every chunk how many vertices precede it (a face may only
+  // use vertices defined before it: Loader.cpp indexes the vector as it grows)
+  std::vector<size_t> v_before(nt + 1, 0), f_before(nt + 1, 0);
+  for (unsigned t = 0; t < nt; t++) {
+    v_before[t + 1] = v_before[t] + chunks[t].vertices.size();
+    f_before[t + 1] = f_before[t] + chunks[t].faces.size() / 3;
+  }
+  std::vector<Vec4> vertices(v_before[nt]);
+  for (unsigned t = 0; t < nt; t++)
+    if (!chunks[t].vertices.empty()) memcpy(&vertices[v_before[t]], chunks[t].vertices.data(), sizeof(Vec4) * chunks[t].vertices.size());
+  tris.resize(f_before[nt]);
+  const Vec4 blue{0.0f, 0.2f, 0.4f, 0.5f};         // Loader.cpp:20
   const Vec4 translate{-0.4f, 1.15f, -0.7f, 1.0f}; // Loader.cpp:48
-  const char *p = buf.c_str(), *end = p + buf.size();
-  while (p < end) {
-    const char *eol = (const char *)memchr(p, '\n', (size_t)(end - p));
-    if (!eol) eol = end;
-    const char *q = p;
-    while (q < eol && (*q == ' ' || *q == '\t' || *q == '\r')) q++;
-    const char *tok = q;
-    while (q < eol && !(*q == ' ' || *q == '\t' || *q == '\r')) q++;
-    const size_t toklen = (size_t)(q - tok);
-    if (toklen == 1 && *tok == 'v') {
-      char *e;
-      const float x = strtof(q, &e);
-      const float y = strtof(e, &e);
-      const float z = strtof(e, &e);
-      vertices.push_back(Vec4{1.5f * x, 1.5f * y, 1.5f * z, 1.0f});
-    } else if (toklen == 1 && *tok == 'f') {
-      char *e;
-      const long a = strtol(q, &e, 10), b = strtol(e, &e, 10), c = strtol(e, &e, 10);
-      const long nv = (long)vertices.size();
-      if (a < 1 || b < 1 || c < 1 || a > nv || b > nv || c > nv) return false;
-      Tri t{vertices[(size_t)a - 1], vertices[(size_t)b - 1], vertices[(size_t)c - 1], Vec4{0, 0, 0, 1}, blue};
-      compute_normal(t);  // from the scaled, untransformed vertices; kept as is
-      Vec4 *vs[3] = {&t.v1, &t.v2, &t.v0};
+  auto build = [&](unsigned t) {
+    ObjChunk &ch = chunks[t];
+    // vertices visible to the faces of this chunk: all of the earlier chunks; inside the chunk the
+    // interleaving of v and f lines is not tracked, so (conservatively, like the usual OBJ layout) the
+    // chunk's own vertices count as well — an index beyond them is an error as in the reference
+    const long nv = (long)v_before[t + 1];
+    for (size_t k = 0; k < ch.faces.size() / 3; k++) {
+      const long a = ch.faces[3 * k], b = ch.faces[3 * k + 1], c = ch.faces[3 * k + 2];
+      if (a < 1 || b < 1 || c < 1 || a > nv || b > nv || c > nv) {
+        ch.bad_face = true;
+        return;
+      }
+      Tri tr{vertices[(size_t)a - 1], vertices[(size_t)b - 1], vertices[(size_t)c - 1], Vec4{0, 0, 0, 1}, blue};
+      compute_normal(tr);  // from the scaled, untransformed vertices; kept as is
+      Vec4 *vs[3] = {&tr.v1, &tr.v2, &tr.v0};
       for (Vec4 *v : vs) {
         v->x = (-1.f) * v->x + translate.x;
         v->y = (-1.f) * v->y + translate.y;
         v->z = (-1.f) * v->z + translate.z;
         v->w = (-1.f) * v->w + translate.w;
       }
-      tris.push_back(t);
+      tris[f_before[t] + k] = tr;
     }
-    p = eol + 1;
+  };
+  {
+    std::vector<std::thread> pool;
+    for (unsigned t = 1; t < nt; t++) pool.emplace_back(build, t);
+    build(0);
+    for (auto &th : pool) th.join();
   }
+  for (unsigned t = 0; t < nt; t++)
+    if (chunks[t].bad_face) return false;
   return true;
 }
 
@@ -200,9 +265,22 @@ int uob_load_test_model(float *verts, float *normals, float *colors, int cap) {
 }
 
 int uob_load_obj(const char *path, float *verts, float *normals, float *colors, int cap) {
-  std::vector<Tri> tris;
-  if (!path || !parse_obj(path, tris)) return INT_MIN;
-  return flatten(tris, verts, normals, colors, cap);
+  // the two-pass use (cap = 0 to size the buffers, then the real call) parses the file once
+  static thread_local std::string cached_path;
+  static thread_local std::vector<Tri> cached;
+  if (!path) return INT_MIN;
+  if (cached_path != path || cap == 0) {
+    cached.clear();
+    cached_path.clear();
+    if (!parse_obj(path, cached)) return INT_MIN;
+    cached_path = path;
+  }
+  const int rc = flatten(cached, verts, normals, colors, cap);
+  if (rc >= 0) {  // delivered: drop the copy
+    std::vector<Tri>().swap(cached);
+    cached_path.clear();
+  }
+  return rc;
 }
 
 void uob_rot_matrix(float yaw, float pitch, float rot12[12]) {
