@@ -384,6 +384,22 @@ def run_ours(args, cfg) -> int:
         e2e_line = {"value": round(counts["rays"] / t_e2e / 1e6, 1), "unit": UNIT, "ms_per_step": round(t_e2e * 1e3, 4),
                     "h2d_bytes_per_step": 84, "d2h_bytes_per_step": W * H * 4,
                     "api": "rt_render (blocking: per-frame args + kernel + read-back into pinned host memory)"}
+        # the same through the pipelined pair rt_render_begin / rt_render_end (a render loop: the read-back of
+        # frame k overlaps the kernel of frame k+1; every frame still lands in host memory)
+        host2 = torch.empty(H * W, dtype=torch.int32).pin_memory()
+        bufs = [hp, host2.data_ptr()]
+        r.render_begin(rot, cam4, light4, cfg.focal, bufs[0])
+        for i in range(1, 4):
+            r.render_begin(rot, cam4, light4, cfg.focal, bufs[i & 1])
+            r.render_end()
+        t0 = time.perf_counter()
+        for i in range(args.steps):
+            r.render_begin(rot, cam4, light4, cfg.focal, bufs[i & 1])
+            r.render_end()
+        t_pipe = (time.perf_counter() - t0) / args.steps
+        r.render_end()
+        e2e_line["pipelined"] = {"value": round(counts["rays"] / t_pipe / 1e6, 1), "unit": UNIT, "ms_per_step": round(t_pipe * 1e3, 4),
+                                 "api": "rt_render_begin / rt_render_end, two frames in flight"}
     else:
         # every rank: render tile -> all-gather -> rank 0 reads the whole frame back
         def step_e2e():

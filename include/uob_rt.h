@@ -17,6 +17,7 @@
 #ifndef UOB_RT_H
 #define UOB_RT_H
 
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
@@ -95,6 +96,24 @@ int rt_upload_scene(rt_ctx *ctx, const float *verts_xyzw, const float *normals_x
  * (cudaHostAlloc / cudaHostRegister) for the overlap and full copy speed. */
 int rt_render(rt_ctx *ctx, const float rot12[12], const float cam[4], const float light[4],
               float focal_length, uint32_t *host_argb);
+
+/* Page-locked host memory for frame buffers — what `screen->buffer = new uint32_t[W*H]`
+ * (SDLauxiliary.h:105) should become: read-back into pageable memory is several times slower and cannot
+ * overlap with rendering.  rt_host_free(NULL) is a no-op. */
+void *rt_host_alloc(size_t bytes);
+void rt_host_free(void *p);
+
+/* Pipelined form of rt_render for a render loop (the reference's main loop renders frame after
+ * frame, skeleton.cpp:117-138): rt_render_begin enqueues the frame and its read-back into host_argb
+ * and returns at once; rt_render_end blocks until the OLDEST frame begun and not yet ended is
+ * complete in its host buffer.  Up to two frames may be in flight (two device frame buffers): the
+ * read-back of frame k overlaps the kernel of frame k+1, so a loop
+ *     begin(f0); for k: begin(f[k+1]); end();  ...  end();
+ * runs at max(kernel, copy) per frame instead of their sum.  Frames are identical to rt_render's.
+ * Each host buffer must stay untouched until its rt_render_end returns. */
+int rt_render_begin(rt_ctx *ctx, const float rot12[12], const float cam[4], const float light[4],
+                    float focal_length, uint32_t *host_argb);
+int rt_render_end(rt_ctx *ctx);
 
 /* Kernel only, asynchronous, no read-back.  dev_argb: device pointer to the
  * WHOLE frame (width*height uint32) — this context's tile is written at row

@@ -40,6 +40,10 @@ RT_SYMBOLS = {
     "rt_create": (ctypes.c_void_p, [ctypes.POINTER(RtConfig)]),
     "rt_upload_scene": (ctypes.c_int, [ctypes.c_void_p, c_float_p, c_float_p, c_float_p, ctypes.c_int]),
     "rt_render": (ctypes.c_int, [ctypes.c_void_p, c_float_p, c_float_p, c_float_p, ctypes.c_float, ctypes.c_void_p]),
+    "rt_host_alloc": (ctypes.c_void_p, [ctypes.c_size_t]),
+    "rt_host_free": (None, [ctypes.c_void_p]),
+    "rt_render_begin": (ctypes.c_int, [ctypes.c_void_p, c_float_p, c_float_p, c_float_p, ctypes.c_float, ctypes.c_void_p]),
+    "rt_render_end": (ctypes.c_int, [ctypes.c_void_p]),
     "rt_render_device": (ctypes.c_int, [ctypes.c_void_p, c_float_p, c_float_p, c_float_p, ctypes.c_float,
                                         ctypes.c_void_p, ctypes.c_void_p]),
     "rt_set_stream": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p]),

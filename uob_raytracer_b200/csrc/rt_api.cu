@@ -95,6 +95,15 @@ static int free_ctx(rt_ctx *ctx) {
     if (ctx->band_done[b]) cudaEventDestroy(ctx->band_done[b]);
   }
   if (ctx->band_start) cudaEventDestroy(ctx->band_start);
+  if (ctx->copy_stream) {
+    cudaStreamSynchronize(ctx->copy_stream);
+    cudaStreamDestroy(ctx->copy_stream);
+  }
+  for (int sl = 0; sl < 2; sl++) {
+    if (ctx->slot_kernel_done[sl]) cudaEventDestroy(ctx->slot_kernel_done[sl]);
+    if (ctx->slot_copy_done[sl]) cudaEventDestroy(ctx->slot_copy_done[sl]);
+  }
+  if (ctx->d_frame_alt) cudaFree(ctx->d_frame_alt);
   if (ctx->ev0) cudaEventDestroy(ctx->ev0);
   if (ctx->ev1) cudaEventDestroy(ctx->ev1);
   if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
@@ -342,6 +351,69 @@ int rt_render(rt_ctx *ctx, const float rot12[12], const float cam[4], const floa
   RT_CUDA(ctx, cudaEventRecord(ctx->ev1, ctx->stream), "recording stop event");
   ctx->timed = true;
   RT_CUDA(ctx, cudaStreamSynchronize(ctx->stream), "reading screen buffer data");
+  return RT_OK;
+}
+
+void *rt_host_alloc(size_t bytes) {
+  void *p = nullptr;
+  if (cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocPortable) != cudaSuccess) {
+    cudaGetLastError();
+    return nullptr;
+  }
+  return p;
+}
+
+void rt_host_free(void *p) {
+  if (p) cudaFreeHost(p);
+}
+
+int rt_render_begin(rt_ctx *ctx, const float rot12[12], const float cam[4], const float light[4], float focal, uint32_t *host_argb) {
+  if (!ctx) return RT_ERR_INVALID;
+  if (!host_argb) {
+    ctx->err = "rt_render_begin: host_argb is NULL";
+    return RT_ERR_INVALID;
+  }
+  if (ctx->frames_begun - ctx->frames_ended >= 2) {
+    ctx->err = "rt_render_begin: two frames are already in flight; call rt_render_end first";
+    return RT_ERR_INVALID;
+  }
+  RT_CUDA(ctx, cudaSetDevice(ctx->cfg.device), "selecting device");
+  const size_t frame_words = (size_t)ctx->cfg.width * ctx->cfg.height;
+  if (!ctx->copy_stream) {  // first use: second frame buffer, copy stream, events
+    RT_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking), "creating copy stream");
+    for (int sl = 0; sl < 2; sl++) {
+      RT_CUDA(ctx, cudaEventCreateWithFlags(&ctx->slot_kernel_done[sl], cudaEventDisableTiming), "creating event");
+      RT_CUDA(ctx, cudaEventCreateWithFlags(&ctx->slot_copy_done[sl], cudaEventDisableTiming), "creating event");
+    }
+    RT_CUDA(ctx, cudaMalloc(&ctx->d_frame_alt, sizeof(uint32_t) * frame_words), "creating second screen buffer");
+  }
+  const int sl = (int)(ctx->frames_begun & 1);
+  uint32_t *dst = sl ? ctx->d_frame_alt : ctx->d_frame;
+  // the kernel may overwrite this slot only after its previous read-back (two frames ago) finished
+  if (ctx->slot_busy[sl]) RT_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->slot_copy_done[sl], 0), "ordering the frame slot");
+  int rc = render_impl(ctx, rot12, cam, light, focal, dst, ctx->stream);
+  if (rc != RT_OK) return rc;
+  RT_CUDA(ctx, cudaEventRecord(ctx->slot_kernel_done[sl], ctx->stream), "recording kernel completion");
+  RT_CUDA(ctx, cudaStreamWaitEvent(ctx->copy_stream, ctx->slot_kernel_done[sl], 0), "ordering the read-back");
+  const size_t off = (size_t)ctx->row0 * ctx->cfg.width, cnt = (size_t)ctx->rows * ctx->cfg.width;
+  RT_CUDA(ctx, cudaMemcpyAsync(host_argb, dst + off, sizeof(uint32_t) * cnt, cudaMemcpyDeviceToHost, ctx->copy_stream),
+          "reading screen buffer data");
+  RT_CUDA(ctx, cudaEventRecord(ctx->slot_copy_done[sl], ctx->copy_stream), "recording read-back completion");
+  ctx->slot_busy[sl] = true;
+  ctx->frames_begun++;
+  return RT_OK;
+}
+
+int rt_render_end(rt_ctx *ctx) {
+  if (!ctx) return RT_ERR_INVALID;
+  if (ctx->frames_begun == ctx->frames_ended) {
+    ctx->err = "rt_render_end: no frame in flight";
+    return RT_ERR_INVALID;
+  }
+  RT_CUDA(ctx, cudaSetDevice(ctx->cfg.device), "selecting device");
+  const int sl = (int)(ctx->frames_ended & 1);
+  RT_CUDA(ctx, cudaEventSynchronize(ctx->slot_copy_done[sl]), "reading screen buffer data");
+  ctx->frames_ended++;
   return RT_OK;
 }
 

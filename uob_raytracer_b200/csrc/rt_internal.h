@@ -27,6 +27,12 @@ struct rt_ctx {
   cudaStream_t band_stream[kBands] = {};
   cudaEvent_t band_done[kBands] = {};
   cudaEvent_t band_start = nullptr;
+  // rt_render_begin / rt_render_end: two frame slots, a copy stream, per-slot events
+  uint32_t *d_frame_alt = nullptr;
+  cudaStream_t copy_stream = nullptr;
+  cudaEvent_t slot_kernel_done[2] = {}, slot_copy_done[2] = {};
+  bool slot_busy[2] = {false, false};
+  unsigned long long frames_begun = 0, frames_ended = 0;
   bool timed = false;
   uint32_t *d_frame = nullptr;  // whole frame, W*H
   // Brute-force scene: one float4 buffer, [ta|tb|tc|tn|tcol] x n, [sa|sb|sc] x n_sh (generic kernel),

@@ -98,6 +98,18 @@ class Renderer:
         self._check(self._lib.rt_render(self._ctx, rot12.ctypes.data_as(c_float_p), cam4.ctypes.data_as(c_float_p),
                                         light4.ctypes.data_as(c_float_p), focal, host_ptr))
 
+    def render_begin(self, rot12, cam4, light4, focal: float, host_ptr: int) -> None:
+        """Pipelined rt_render: enqueue the frame and its read-back into host_ptr, return at once (<= 2 in flight)."""
+        r, c, l = _f32(rot12, 12), _f32(cam4, 3), _f32(light4, 3)
+        c4, l4 = np.zeros(4, np.float32), np.zeros(4, np.float32)
+        c4[:3], l4[:3] = c[:3], l[:3]
+        self._check(self._lib.rt_render_begin(self._ctx, r.ctypes.data_as(c_float_p), c4.ctypes.data_as(c_float_p),
+                                              l4.ctypes.data_as(c_float_p), focal, host_ptr))
+
+    def render_end(self) -> None:
+        """Block until the oldest frame begun with render_begin is complete in its host buffer."""
+        self._check(self._lib.rt_render_end(self._ctx))
+
     def render_device(self, rot12, cam4, light4, focal: float, dev_ptr: int = 0, stream: int = 0) -> None:
         """Asynchronous kernel launch only; dev_ptr = whole-frame device buffer (0 = the context's own)."""
         self._check(self._lib.rt_render_device(self._ctx, rot12.ctypes.data_as(c_float_p),
