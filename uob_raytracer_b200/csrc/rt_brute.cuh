@@ -315,6 +315,8 @@ template <class T> struct BruteTracer {
     t.sc = sc;
     return t;
   }
+  // primary ray of the fast policy: reference arithmetic (see shade_pixel)
+  __device__ __forceinline__ void primary_strict(V3<sfloat> cam, V3<sfloat> dir, HitRec<sfloat> &hit) const { strict().closest(cam, dir, hit); }
 
   __device__ __forceinline__ void closest(V3<T> start, V3<T> dir, HitRec<T> &hit) const {
     ClosestState<T> cs;
@@ -479,7 +481,7 @@ __device__ __forceinline__ uint32_t shade_pixel(const Tracer &tr, const FramePar
         hs.color = hit.color;
         hs.point = V3<S>(S(0.0f), S(0.0f), S(0.0f));
         hs.normal = hs.point;
-        tr.strict().closest(V3<S>(S(p.cam[0]), S(p.cam[1]), S(p.cam[2])), ds, hs);
+        tr.primary_strict(V3<S>(S(p.cam[0]), S(p.cam[1]), S(p.cam[2])), ds, hs);
         dir = V3<T>(ds.x.v, ds.y.v, ds.z.v);
         hit.id = hs.id;
         hit.point = V3<T>(hs.point.x.v, hs.point.y.v, hs.point.z.v);

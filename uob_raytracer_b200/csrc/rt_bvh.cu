@@ -192,12 +192,58 @@ __global__ void bvh_emit_kernel(int n, const int *__restrict__ left, const int *
 // draw kernel
 // ---------------------------------------------------------------------------------------------
 
+constexpr int kBigPrimaryMax = 32;  // big triangles handled by the camera-constant filter (one warp bins them)
+
 template <class T, int CH>
 __global__ void __launch_bounds__(kThreads) draw_bvh_kernel(const __grid_constant__ FrameParams p, const __grid_constant__ BvhView bv) {
+  __shared__ float4 s_prim[3 * kBigPrimaryMax];
+  __shared__ int s_plist[kBigPrimaryMax];
+  __shared__ int s_nlist;
   int x, y, tx, ty;
-  if (!pixel_of_thread(p, x, y, tx, ty)) return;
+  const bool in_frame = pixel_of_thread(p, x, y, tx, ty);
   BvhTracer<T> tr;
   tr.bv = bv;
+  const int n_big = bv.n - bv.n_bvh;
+  if constexpr (!is_strict<T>::value) {
+    if (n_big > 0 && n_big <= kBigPrimaryMax) {  // uniform
+      if (threadIdx.x < 32) {
+        // per-frame camera constants of the big triangles and their binning against this block's tile
+        // (same as the prologue of draw_fast_kernel)
+        const int lane = threadIdx.x, A = p.A;
+        const float SW = (float)p.W, SH = (float)p.H, fA = (float)A;
+        const float vx0 = (float)(tx * A) - SW * fA * 0.5f, vy0 = (float)(ty * A) - SH * fA * 0.5f;
+        const float vx1 = vx0 + (float)(kTileW * A - 1), vy1 = vy0 + (float)(kTileH * A - 1);
+        V3<float> dc[4];
+        float dmax = 0.0f;
+#pragma unroll
+        for (int c = 0; c < 4; c++) {
+          const float vx = (c & 1) ? vx1 : vx0, vy = (c & 2) ? vy1 : vy0;
+          dc[c] = V3<float>(p.rot[0] * vx + p.rot[1] * vy + p.rot[2] * p.focal, p.rot[3] * vx + p.rot[4] * vy + p.rot[5] * p.focal,
+                            p.rot[6] * vx + p.rot[7] * vy + p.rot[8] * p.focal);
+          dmax = fmaxf(dmax, sqrtf(dot(dc[c], dc[c])));
+        }
+        dmax *= 1.001f;
+        bool keep = false;
+        if (lane < n_big) {
+          SceneView g;
+          g.ta = bv.tri_a + bv.n_bvh;
+          g.tb = bv.tri_b + bv.n_bvh;
+          g.tc = bv.tri_c + bv.n_bvh;
+          primary_constants(g, s_prim, V3<float>(p.cam[0], p.cam[1], p.cam[2]), lane);
+          keep = tile_may_hit(s_prim, lane, dc, dmax);
+        }
+        const unsigned ballot = __ballot_sync(0xffffffffu, keep);
+        if (keep) s_plist[__popc(ballot & ((1u << lane) - 1u))] = lane;
+        if (lane == 0) s_nlist = __popc(ballot);
+      }
+      __syncthreads();
+      tr.big.prim = s_prim;
+      tr.big.plist = s_plist;
+      tr.big.n_list = s_nlist;
+      tr.big.n_big = n_big;
+    }
+  }
+  if (!in_frame) return;
   p.out[(size_t)y * p.W + x] = shade_pixel<T, CH, BvhTracer<T>>(tr, p, x, y);
 }
 

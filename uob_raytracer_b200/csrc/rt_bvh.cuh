@@ -20,7 +20,7 @@
 // fetches are shared, a leaf runs the same (origin, triangle) x CH-rays test as the brute-force
 // path on the rays that reach it.
 #pragma once
-#include "rt_brute.cuh"
+#include "rt_fast.cuh"
 
 namespace rt {
 
@@ -53,22 +53,67 @@ __device__ __forceinline__ float box_entry(float lox, float loy, float loz, floa
   return (tn <= tf) ? tn : -1.0f;
 }
 
+// Shared-memory helper of the fast policy: the big triangles (room walls) seen from the camera, with the
+// per-frame constants and per-tile binning of the brute-force fast path (rt_fast.cuh), so that a primary ray
+// filters them with three dot products each and confirms survivors strictly.  Slot numbers are relative to
+// bv.n_bvh.  n_big < 0: not available (too many big triangles) -> plain strict loop.
+struct BvhBigPrimary {
+  const float4 *prim;
+  const int *plist;
+  int n_list;
+  int n_big;
+};
+
 template <class T> struct BvhTracer {
   BvhView bv;
+  BvhBigPrimary big{nullptr, nullptr, 0, -1};
   __device__ __forceinline__ BvhTracer<sfloat> strict() const {  // same tree, reference arithmetic
     BvhTracer<sfloat> t;
     t.bv = bv;
     return t;
   }
 
+  // primary ray of the fast policy: reference arithmetic; the big triangles through the camera-constant filter
+  __device__ void primary_strict(V3<sfloat> cam, V3<sfloat> dir, HitRec<sfloat> &hit) const {
+    BvhTracer<sfloat> t;
+    t.bv = bv;
+    if (big.n_big < 0) {
+      t.closest(cam, dir, hit);
+      return;
+    }
+    FastScene fs;
+    fs.prim = big.prim;
+    fs.plist = big.plist;
+    fs.n_prim = big.n_list;
+    int bi;
+    float bt, bu, bv_;
+    primary_triangles(fs, V3<float>(dir.x.v, dir.y.v, dir.z.v), bi, bt, bu, bv_);  // strict t,u,v of the closest big triangle
+    ClosestState<sfloat> cs;
+    cs.reset();
+    if (bi >= 0) {
+      cs.t = sfloat(bt);
+      cs.u = sfloat(bu);
+      cs.v = sfloat(bv_);
+      cs.slot = bv.n_bvh + bi;
+      cs.id = bv.tri_id[cs.slot];
+    }
+    t.closest_from(cam, dir, hit, cs, false);
+  }
+
   // kernels.cl:92-166 / :168-241
   __device__ void closest(V3<T> start, V3<T> dir, HitRec<T> &hit) const {
     ClosestState<T> cs;
     cs.reset();
+    closest_from(start, dir, hit, cs, true);
+  }
+
+  // continue a closest-hit search from state cs (test_big: the linear list has not been searched yet)
+  __device__ void closest_from(V3<T> start, V3<T> dir, HitRec<T> &hit, ClosestState<T> cs, bool test_big) const {
     const V3<T> nd = -dir;
     // the big triangles, linearly
-    for (int s = bv.n_bvh; s < bv.n; s++)
-      closest_tri_test<T, false>(bv.tri_a[s], bv.tri_b[s], bv.tri_c[s], start, nd, bv.tri_id[s], s, cs);
+    if (test_big)
+      for (int s = bv.n_bvh; s < bv.n; s++)
+        closest_tri_test<T, false>(bv.tri_a[s], bv.tri_b[s], bv.tri_c[s], start, nd, bv.tri_id[s], s, cs);
     if (bv.n_bvh > 0) {
       const float ox = raw(start.x), oy = raw(start.y), oz = raw(start.z);
       const float ix = safe_rcp_dir(raw(dir.x)), iy = safe_rcp_dir(raw(dir.y)), iz = safe_rcp_dir(raw(dir.z));
