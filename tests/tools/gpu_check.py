@@ -1,6 +1,6 @@
 """Ad-hoc GPU check: strict/fast parity against the oracle + kernel timings. Run under gpurun."""
 import sys, time, os, json
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import numpy as np
 import uob_raytracer_b200 as u
 from oracle import bind as ob
@@ -21,7 +21,7 @@ big = {"cfg3": (3840, 2160, 4, 10, 4), "cfg5": (7680, 4320, 2, 10, 10)}
 if len(sys.argv) > 1:
     cases = [c for c in cases if c[0] in sys.argv[1:]]
 import json as _json
-counts = _json.load(open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden", "ray_counts.json")))
+counts = _json.load(open(os.path.join(os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))), "tests", "golden", "ray_counts.json")))
 for name in [a for a in sys.argv[1:] if a in big]:
     W, H, A, S, B = big[name]
     f = 1100.0 * A * H / 1024
