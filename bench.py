@@ -283,14 +283,28 @@ def run_ours(args, cfg) -> int:
     token = torch.zeros(1, dtype=torch.int32, device=f"cuda:{local_rank}")
     peer_ptr = 0
     fno = [0]  # frame number, the value the hand-over flags count up to
+    r = None
     if gather in ("p2p", "p2p-nccl"):
         r = u.Renderer(W, H, cfg.aa, cfg.shadow_samples, cfg.max_bounces, device=local_rank, block_stride=world,
                        block_phase=rank)
         handle = [r.ipc_export_frame() if rank == 0 else None]
         dist.broadcast_object_list(handle, src=0)
-        target = r.device_frame_ptr if rank == 0 else r.ipc_open_frame(handle[0])
-        peer_ptr = 0 if rank == 0 else target
-    else:
+        ok = torch.ones(1, dtype=torch.int32, device=f"cuda:{local_rank}")
+        try:
+            target = r.device_frame_ptr if rank == 0 else r.ipc_open_frame(handle[0])
+            peer_ptr = 0 if rank == 0 else target
+        except u.RtError as exc:  # CUDA IPC not available between these processes
+            print(f"bench.py: rank {rank}: {exc}; falling back to --gather nccl", file=sys.stderr)
+            ok.zero_()
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+        if int(ok.item()) == 0:
+            if peer_ptr:
+                r.ipc_close_frame(peer_ptr)
+                peer_ptr = 0
+            r.close()
+            r = None
+            gather = "nccl"
+    if r is None:
         r = u.Renderer(W, H, cfg.aa, cfg.shadow_samples, cfg.max_bounces, device=local_rank, row0=row0, rows=rows)
         target = frame.data_ptr()
     r.upload_scene(scene)

@@ -165,8 +165,14 @@ rt_ctx *rt_create(const rt_config *cfg) {
   ctx->stream = ctx->own_stream;
   if ((e = cudaEventCreate(&ctx->ev0)) != cudaSuccess) return fail("creating event", e);
   if ((e = cudaEventCreate(&ctx->ev1)) != cudaSuccess) return fail("creating event", e);
+  // earlier bands get the higher stream priority, so that the bands finish roughly in order and each
+  // read-back starts while the later bands still render
+  int prio_least = 0, prio_greatest = 0;
+  cudaDeviceGetStreamPriorityRange(&prio_least, &prio_greatest);
   for (int b = 0; b < rt_ctx::kBands; b++) {
-    if ((e = cudaStreamCreateWithFlags(&ctx->band_stream[b], cudaStreamNonBlocking)) != cudaSuccess) return fail("creating stream", e);
+    int prio = prio_greatest + b;
+    if (prio > prio_least) prio = prio_least;
+    if ((e = cudaStreamCreateWithPriority(&ctx->band_stream[b], cudaStreamNonBlocking, prio)) != cudaSuccess) return fail("creating stream", e);
     if ((e = cudaEventCreateWithFlags(&ctx->band_done[b], cudaEventDisableTiming)) != cudaSuccess) return fail("creating event", e);
   }
   if ((e = cudaEventCreateWithFlags(&ctx->band_start, cudaEventDisableTiming)) != cudaSuccess) return fail("creating event", e);
