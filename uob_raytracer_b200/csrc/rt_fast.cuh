@@ -235,12 +235,17 @@ __device__ __forceinline__ int shadow_lit_count(const FastScene &sc, V3<float> s
                                                 const J &j, unsigned valid_mask) {
   constexpr unsigned FULL = (CH >= 32) ? 0xffffffffu : ((1u << CH) - 1u);
   unsigned occ = ~valid_mask & FULL;  // padding samples of a ragged chunk count as occluded (ignored by the caller)
-  float dd[CH];                       // |d_k|^2
+  float dd[CH];                       // |d_k|^2, filled on first use: most points never reach a per-sample test
+  bool have_dd = false;
+  auto need_dd = [&]() {
+    if (have_dd) return;
+    have_dd = true;
 #pragma unroll
-  for (int k = 0; k < CH; k++) {
-    const float ddx = r.x + j.jx(k), ddy = r.y + j.jy(k), ddz = r.z + j.jz(k);
-    dd[k] = (ddx * ddx + ddy * ddy) + ddz * ddz;
-  }
+    for (int k = 0; k < CH; k++) {
+      const float ddx = r.x + j.jx(k), ddy = r.y + j.jy(k), ddz = r.z + j.jz(k);
+      dd[k] = (ddx * ddx + ddy * ddy) + ddz * ddz;
+    }
+  };
   // |r| / |d_s| <= R / (R - jmax); no bound (k huge) when the light is closer than 2 jmax
   const float R = sqrt_approx(radius_sq);
   const float inv_r2 = rcp_approx(radius_sq);
@@ -271,6 +276,7 @@ __device__ __forceinline__ int shadow_lit_count(const FastScene &sc, V3<float> s
     }
     const float q1 = num * num * inv_r2;  // t^2 |d|^2 < r^2  <=>  q1 |d|^2 < dn^2
     const unsigned numb = __float_as_uint(num);
+    need_dd();
 #pragma unroll
     for (int k = 0; k < CH; k++) {
       // det A = -dn;  t = -num/dn;  u = E1/dn;  v = E2/dn
@@ -300,6 +306,7 @@ __device__ __forceinline__ int shadow_lit_count(const FastScene &sc, V3<float> s
     const float perp2 = LL - Lr * Lr * inv_r2;
     const float lim = kSlack * sqrt_approx(cr.w) + sqrt_approx(LL) * (kk * kJitterMax * rcp_approx(R));
     if (perp2 > lim * lim) continue;
+    need_dd();
 #pragma unroll
     for (int k = 0; k < CH; k++) {
       if ((occ >> k) & 1u) continue;
