@@ -225,9 +225,9 @@ int rt_upload_scene(rt_ctx *ctx, const float *verts, const float *normals, const
   // Per-triangle constants, computed with the single-rounded operations the
   // reference kernel performs per ray (kernels.cl:102-104 and the cofactors of
   // det, :31-35).  volatile keeps the host compiler from contracting a*b-c*d.
-  std::vector<float4> h(5 * (size_t)n + 7 * (size_t)n_sh);
+  std::vector<float4> h(5 * (size_t)n + 8 * (size_t)n_sh);
   float4 *ta = h.data(), *tb = ta + n, *tc = tb + n, *tn = tc + n, *tcol = tn + n;
-  float4 *sa = tcol + n, *sb = sa + n_sh, *sc = sb + n_sh, *rec = sc + n_sh;
+  float4 *sa = tcol + n, *sb = sa + n_sh, *sc = sb + n_sh, *rec = sc + n_sh, *bnd = rec + 4 * (size_t)n_sh;
   int k = 0;
   for (int i = 0; i < n; i++) {
     const float *v0 = verts + 12 * (size_t)i, *v1 = v0 + 4, *v2 = v0 + 8;
@@ -251,6 +251,16 @@ int rt_upload_scene(rt_ctx *ctx, const float *verts, const float *normals, const
       rec[4 * k + 1] = make_float4(c0, c1, c2, 0.0f);
       rec[4 * k + 2] = make_float4(e1x, e1y, e1z, kj * sqrtf(e1x * e1x + e1y * e1y + e1z * e1z));
       rec[4 * k + 3] = make_float4(e2x, e2y, e2z, kj * sqrtf(e2x * e2x + e2y * e2y + e2z * e2z));
+      {  // bounding sphere (centroid, farthest vertex) for the warp-level beam cull
+        const float cx = (v0[0] + v1[0] + v2[0]) / 3.0f, cy = (v0[1] + v1[1] + v2[1]) / 3.0f, cz = (v0[2] + v1[2] + v2[2]) / 3.0f;
+        float r2 = 0.0f;
+        const float *vs[3] = {v0, v1, v2};
+        for (const float *v : vs) {
+          const float dx = v[0] - cx, dy = v[1] - cy, dz = v[2] - cz, d2 = dx * dx + dy * dy + dz * dz;
+          r2 = d2 > r2 ? d2 : r2;
+        }
+        bnd[k] = make_float4(cx, cy, cz, sqrtf(r2) * 1.0001f);
+      }
       k++;
     }
   }

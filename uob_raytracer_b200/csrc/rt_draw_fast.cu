@@ -22,13 +22,14 @@ __global__ void __launch_bounds__(kThreads, RT_MINBLOCKS) draw_fast_kernel(const
   float4 *const gen = smem;
   float4 *const prim = smem + 5 * n;
   float4 *const shad = prim + 3 * n;
-  int *const plist = reinterpret_cast<int *>(shad + 4 * n_sh);
+  float4 *const sbound = shad + 4 * n_sh;  // bounding sphere of every shadow caster
+  int *const plist = reinterpret_cast<int *>(sbound + n_sh);
   int *const full_list = plist + n;  // 0, 1, ..., n_sh-1: "test every caster"
   // per-thread columns after the lists: parked primary hits (4 x 7 words), then the jitters (SINGLE only)
   float *const rec_base = reinterpret_cast<float *>(smem + scene_smem_float4(n, n_sh));
   float *const jit_base = rec_base + 4 * 7 * kThreads;
   for (int i = threadIdx.x; i < 5 * n; i += kThreads) gen[i] = scene[i];
-  for (int i = threadIdx.x; i < 4 * n_sh; i += kThreads) shad[i] = scene[5 * n + 3 * n_sh + i];
+  for (int i = threadIdx.x; i < 5 * n_sh; i += kThreads) shad[i] = scene[5 * n + 3 * n_sh + i];  // records + bounding spheres
   for (int i = threadIdx.x; i < n_sh; i += kThreads) full_list[i] = i;
   FastScene sc;
   sc.g.ta = gen;
@@ -223,7 +224,7 @@ __global__ void __launch_bounds__(kThreads, RT_MINBLOCKS) draw_fast_kernel(const
         int count = 0;
         for (int c0 = 0; c0 < n_sh; c0 += n_act) {
           const int c = c0 + rank;
-          const bool keep = c < n_sh && box_may_be_shadowed_by(shad, c, lo, hi, light);
+          const bool keep = c < n_sh && box_may_be_shadowed_by(shad, sbound, c, lo, hi, light);
           const unsigned bal = __ballot_sync(warp_mask, keep);
           if (keep) s_wlist[warp][count + __popc(bal & ((1u << lane) - 1u))] = c;
           count += __popc(bal);

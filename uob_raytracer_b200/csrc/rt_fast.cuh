@@ -75,7 +75,8 @@ __device__ __forceinline__ float float_of_ord(unsigned o) {
 // num(P) = (P + bias (L-P) - v0).N and rN(P) = (L-P).N are affine in P, so over the box they stay within
 // +-hN of their centre values, hN = |N|.half-extent; |r|/|d_s| <= k(R) is largest at the box point
 // nearest to the light.  False only if the per-point cull would reject the pair at every point.
-__device__ __forceinline__ bool box_may_be_shadowed_by(const float4 *shad, int c, V3<float> lo, V3<float> hi, V3<float> light) {
+__device__ __forceinline__ bool box_may_be_shadowed_by(const float4 *shad, const float4 *sbound, int c, V3<float> lo, V3<float> hi,
+                                                       V3<float> light) {
   const float4 Q0 = shad[4 * c], Q1 = shad[4 * c + 1];
   const V3<float> ctr((lo.x + hi.x) * 0.5f, (lo.y + hi.y) * 0.5f, (lo.z + hi.z) * 0.5f);
   const V3<float> half((hi.x - lo.x) * 0.5f, (hi.y - lo.y) * 0.5f, (hi.z - lo.z) * 0.5f);
@@ -89,6 +90,23 @@ __device__ __forceinline__ bool box_may_be_shadowed_by(const float4 *shad, int c
               dz = fmaxf(fmaxf(lo.z - light.z, light.z - hi.z), 0.0f);
   const float rmin = sqrtf(dx * dx + dy * dy + dz * dz) * 0.9999f;
   if (!(rmin > 2.0f * kJitterMax)) return true;
+  {
+    // Beam cull: every shadow ray from a point of the box runs inside the convex hull of ball(box centre,
+    // box half-diagonal) and ball(light, 2 jmax) — a cone frustum around the axis centre -> light.  A caster
+    // whose bounding sphere lies outside that hull cannot be hit from anywhere in the box.
+    const float4 bs = sbound[c];
+    const float rb = sqrtf(dot(half, half)) * 1.0001f + 1e-6f, rl = 2.0f * kJitterMax;
+    const float aa = dot(r, r);
+    const V3<float> xc(bs.x - ctr.x, bs.y - ctr.y, bs.z - ctr.z);
+    const float s = fminf(fmaxf(dot(xc, r) / aa, 0.0f), 1.0f);
+    const V3<float> off(xc.x - s * r.x, xc.y - s * r.y, xc.z - s * r.z);
+    const float dist = sqrtf(dot(off, off));
+    const float sin_a = fabsf(rb - rl) * rsqrtf(aa);
+    if (sin_a < 0.999f) {
+      const float cos_a = sqrtf(1.0f - sin_a * sin_a);
+      if ((dist - (rb + (rl - rb) * s)) * cos_a > bs.w + 1e-5f) return false;
+    }
+  }
   const float kk = kSlack * rmin / (rmin - kJitterMax);
   if (num - hN > 0.0f) {        // every point is on the + side of the plane
     const float rhs = Q0.w - (rN - hN);

@@ -36,7 +36,7 @@ struct rt_ctx {
   bool timed = false;
   uint32_t *d_frame = nullptr;  // whole frame, W*H
   // Brute-force scene: one float4 buffer, [ta|tb|tc|tn|tcol] x n, [sa|sb|sc] x n_sh (generic kernel),
-  // then 4 float4 per shadow caster (fast kernel, rt_fast.cuh)
+  // then 4 float4 per shadow caster and n_sh bounding spheres (fast kernel, rt_fast.cuh)
   float4 *d_scene = nullptr;
   int n = 0, n_sh = 0;
   bool have_scene = false;

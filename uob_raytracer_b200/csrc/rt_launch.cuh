@@ -50,7 +50,7 @@ __device__ __forceinline__ bool pixel_of_thread(const FrameParams &p, int &x, in
 const int *tile_order_for(rt_ctx *ctx, int row0, int rows, int grid_x, int n_blocks);
 
 // float4 slots of the scene part of the fast kernel's shared memory (see brute_smem_bytes)
-__host__ __device__ inline int scene_smem_float4(int n, int n_sh) { return 8 * n + 4 * n_sh + (n + n_sh + 3) / 4 + 1; }
+__host__ __device__ inline int scene_smem_float4(int n, int n_sh) { return 8 * n + 5 * n_sh + (n + n_sh + 3) / 4 + 1; }
 
 template <class K>
 inline cudaError_t launch_kernel(K kern, rt_ctx *ctx, const FrameParams &fp_in, cudaStream_t stream) {
