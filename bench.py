@@ -511,6 +511,23 @@ def run_ours(args, cfg) -> int:
                 "sample": ("cfg4 scene at 480x270, one row through the mesh" if mesh else f"{cfg.name}, " + ("all rows" if step == 1 else f"every {step}th row")) +
                           f", best of {i + 1} frames; verbatim kernels.cl via g++ shim (-O2, strict IEEE), all host threads",
                 "ms_per_frame": None if mesh else round(best * step * 1e3, 1)}
+            if not mesh:
+                # Same-box GPU yardstick, still the baseline leg: the reference's own OpenCL kernel on THIS B200 through
+                # NVIDIA's OpenCL driver (oracle/ref_ocl.c; parameter tokens substituted for cfg != HEAD).  Reported, never used.
+                try:
+                    from oracle import bind as ob
+                    if ob.ref_ocl_available():
+                        scene_o, rot_o, cam_o, light_o = scene_and_camera(cfg.name)
+                        _, info = ob.ref_ocl_render(cfg.width, cfg.height, cfg.aa, cfg.shadow_samples, cfg.max_bounces, cfg.focal,
+                                                    scene_o.verts, scene_o.normals, scene_o.colors, rot_o, cam_o, light_o, frames=5)
+                        full = load_counts(cfg.name)["rays"]
+                        line["cpu_baseline"]["same_gpu_opencl"] = {
+                            "what": "reference kernels.cl `draw`, -cl-fast-relaxed-math -cl-mad-enable, NDRange {W,H}/{128,4}",
+                            "device": info["device"], "kernel_ms": round(info["kernel_ms"], 4),
+                            "offload_rendering_ms": round(info["total_ms"], 4),
+                            "value": round(full / info["kernel_ms"] / 1e3, 2), "unit": UNIT}
+                except Exception as e:  # noqa: BLE001 - optional yardstick
+                    line["cpu_baseline"]["same_gpu_opencl"] = {"unavailable": str(e)[:200]}
         print(json.dumps(line), flush=True)
     torch.cuda.synchronize()
     r.synchronize()  # surfaces a timed-out rt_peer_wait

@@ -223,6 +223,61 @@ def ref_load_obj(path: str):
     return _ref_scene_call(lib.ref_load_obj, path.encode(), capacity=4096)
 
 
+def ref_ocl_available() -> bool:
+    return os.path.isfile(os.path.join(REF_DIR, "libref_ocl.so"))
+
+
+def ref_ocl_source(aa: int = 2, shadow_samples: int = 10, max_bounces: int = 10, W: int = 1024, H: int = 1024) -> str:
+    """kernels.cl text for one config.  HEAD values return the embedded text UNMODIFIED; anything else gets the same
+    parameter-token substitutions build_ref.py rewrite (6) applies (the reference's only way to change them is a source
+    edit).  NVIDIA's OpenCL compiler accepts the rest of the file as is (excess initialisers and the &rays pointer are
+    warnings there)."""
+    import re
+    lib = _ref("libref_ocl.so")
+    lib.ref_ocl_source.restype = ctypes.c_char_p
+    src = lib.ref_ocl_source().decode()
+    if (aa, shadow_samples, max_bounces, W, H) == (2, 10, 10, 1024, 1024):
+        return src
+    def sub1(pat, rep):
+        nonlocal src
+        src, k = re.subn(pat, rep, src, flags=re.M)
+        if k != 1:
+            raise RuntimeError(f"rewrite {pat!r} matched {k} times")
+    sub1(r"^#define SCREEN_WIDTH .*$", f"#define SCREEN_WIDTH {W}")
+    sub1(r"^#define SCREEN_HEIGHT .*$", f"#define SCREEN_HEIGHT {H}")
+    sub1(r"^constant char rays_x = \d+;", f"constant char rays_x = {aa};")
+    sub1(r"^constant char rays_y = \d+;", f"constant char rays_y = {aa};")
+    sub1(r"^#define aa_rays \d+", f"#define aa_rays {aa * aa}")
+    sub1(r"const short light_sources = \d+;", f"const short light_sources = {shadow_samples};")
+    sub1(r"const int bounces = \d+;", f"const int bounces = {max_bounces};")
+    return src
+
+
+def ref_ocl_render(W, H, aa, shadow_samples, max_bounces, focal, verts, normals, colors, rot12, cam, light, frames=3):
+    """The reference's own OpenCL kernel on whatever OpenCL GPU the box has (oracle/ref_ocl.c).
+    Returns (frame uint32[H, W], {"kernel_ms", "total_ms", "device"}); raises RuntimeError with the driver's message."""
+    lib = _ref("libref_ocl.so")
+    lib.ref_ocl_last_error.restype = ctypes.c_char_p
+    verts, normals, colors = _f32(verts), _f32(normals), _f32(colors)
+    n = normals.size // 4
+    out = np.zeros((H, W), np.uint32)
+    k_ms, t_ms = ctypes.c_double(0), ctypes.c_double(0)
+    name = ctypes.create_string_buffer(256)
+    src = ref_ocl_source(aa, shadow_samples, max_bounces, W, H).encode()
+    rot12, cam, light = _f32(rot12, (12,)), _f32(cam), _f32(light)
+    cam4, light4 = np.zeros(4, np.float32), np.zeros(4, np.float32)
+    cam4[:3], light4[:3] = cam[:3], light[:3]
+    lib.ref_ocl_render.argtypes = [ctypes.c_char_p, ctypes.c_int, ctypes.c_int, _fp, _fp, _fp, ctypes.c_int, _fp, _fp, _fp,
+                                   ctypes.c_float, ctypes.c_int, _u32p, ctypes.POINTER(ctypes.c_double),
+                                   ctypes.POINTER(ctypes.c_double), ctypes.c_char_p]
+    rc = lib.ref_ocl_render(src, W, H, verts.ctypes.data_as(_fp), normals.ctypes.data_as(_fp), colors.ctypes.data_as(_fp), n,
+                            rot12.ctypes.data_as(_fp), cam4.ctypes.data_as(_fp), light4.ctypes.data_as(_fp),
+                            float(focal), int(frames), out.ctypes.data_as(_u32p), ctypes.byref(k_ms), ctypes.byref(t_ms), name)
+    if rc != 0:
+        raise RuntimeError(f"ref_ocl_render rc={rc}: {lib.ref_ocl_last_error().decode(errors='replace')}")
+    return out, {"kernel_ms": k_ms.value, "total_ms": t_ms.value, "device": name.value.decode(errors="replace")}
+
+
 def frame_hash(frame: np.ndarray) -> str:
     """sha256 over the little-endian ARGB bytes of a frame (first 16 hex digits)."""
     import hashlib

@@ -111,6 +111,22 @@ def build_scene() -> str:
     return out
 
 
+def build_ocl(tmp: str) -> str:
+    """libref_ocl.so: oracle/ref_ocl.c + the UNMODIFIED kernels.cl text embedded as a C string (the GPU box
+    has no /root/reference).  Runs the reference kernel through a real OpenCL driver when one is present."""
+    with open(os.path.join(REFERENCE, "Source", "kernels.cl")) as f:
+        text = f.read()
+    inc = os.path.join(tmp, "kernels_cl_string.inc")
+    with open(inc, "w") as f:
+        for line in text.split("\n"):
+            esc = line.replace("\\", "\\\\").replace('"', '\\"').replace("\t", "\\t").replace("\r", "")
+            f.write('"' + esc + '\\n"\n')
+    out = os.path.join(OUT, "libref_ocl.so")
+    cmd = ["gcc", "-O2", "-fPIC", "-shared", f'-DREF_OCL_SOURCE_INC="{inc}"', os.path.join(HERE, "ref_ocl.c"), "-o", out, "-ldl"]
+    subprocess.check_call(cmd)
+    return out
+
+
 def main(argv: list[str]) -> int:
     if not os.path.isfile(os.path.join(REFERENCE, "Source", "kernels.cl")):
         print(f"build_ref: {REFERENCE} not present — keeping prebuilt oracle/_ref/*.so", file=sys.stderr)
@@ -122,6 +138,7 @@ def main(argv: list[str]) -> int:
     with tempfile.TemporaryDirectory(prefix="uob_ref_") as tmp:
         for aa, s, b in variants:
             print("built", build_variant(aa, s, b, tmp))
+        print("built", build_ocl(tmp))
     print("built", build_scene())
     return 0
 
