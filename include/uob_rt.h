@@ -45,7 +45,11 @@ enum {
   RT_FLAG_FORCE_BVH = 1u << 2,   /* always traverse a BVH, even for 26 triangles */
   /* Count the rays of every frame (rt_get_ray_counts).  Measurement aid: frames are rendered by the
    * generic kernel (same pixels), not the tuned one, so do not time a counting context. */
-  RT_FLAG_COUNT_RAYS = 1u << 3
+  RT_FLAG_COUNT_RAYS = 1u << 3,
+  /* With RT_FLAG_STRICT_IEEE: the reference's plain loop structure (every ray against every triangle), without the
+   * conservative culls the strict path otherwise shares with the fast one.  Same frame bit for bit, several times
+   * slower; kept as the anchor the culled strict path is tested against. */
+  RT_FLAG_REFERENCE_LOOPS = 1u << 4
 };
 
 /* Everything that is a compile-time constant in the reference

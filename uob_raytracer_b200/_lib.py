@@ -24,6 +24,7 @@ RT_FLAG_STRICT_IEEE = 1 << 0
 RT_FLAG_FORCE_BRUTE = 1 << 1
 RT_FLAG_FORCE_BVH = 1 << 2
 RT_FLAG_COUNT_RAYS = 1 << 3
+RT_FLAG_REFERENCE_LOOPS = 1 << 4
 
 
 class RtConfig(ctypes.Structure):

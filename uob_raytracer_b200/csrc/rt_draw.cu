@@ -43,7 +43,8 @@ size_t brute_smem_limit() { return 200 * 1024; }
   } while (0)
 
 cudaError_t launch_draw_brute(rt_ctx *ctx, const FrameParams &fp, cudaStream_t stream) {
-  if (ctx->cfg.flags & RT_FLAG_STRICT_IEEE) {
+  // strict: the culled kernel computes the same frame; RT_FLAG_REFERENCE_LOOPS keeps the plain loop structure
+  if ((ctx->cfg.flags & RT_FLAG_STRICT_IEEE) && ((ctx->cfg.flags & RT_FLAG_REFERENCE_LOOPS) || fp.ray_counters)) {
 #define RT_STRICT(CH) launch_kernel(draw_brute_kernel<sfloat, CH>, ctx, fp, stream)
     RT_DISPATCH_CH(RT_STRICT);
   }

@@ -8,9 +8,11 @@
 
 namespace rt {
 
-// CH shadow samples per chunk, SINGLE = (S == CH).
-template <int CH, bool SINGLE>
-__global__ void __launch_bounds__(kThreads, RT_MINBLOCKS) draw_fast_kernel(const __grid_constant__ FrameParams p,
+// CH shadow samples per chunk, SINGLE = (S == CH).  STRICT = RT_FLAG_STRICT_IEEE: same binning, culls and
+// caster lists, but every test that survives them — and all shading arithmetic — runs the reference's exact
+// operation sequence, so the frame is bit-identical to the reference's (and to draw_brute_kernel<sfloat>).
+template <int CH, bool SINGLE, bool STRICT>
+__global__ void __launch_bounds__(kThreads, STRICT ? 2 : RT_MINBLOCKS) draw_fast_kernel(const __grid_constant__ FrameParams p,
                                                                            const float4 *__restrict__ scene, int n, int n_sh) {
   extern __shared__ float4 smem[];
   __shared__ int s_warp_count[kThreads / 32];
@@ -150,6 +152,8 @@ __global__ void __launch_bounds__(kThreads, RT_MINBLOCKS) draw_fast_kernel(const
       r2(SF(p.rot[6]), SF(p.rot[7]), SF(p.rot[8]));
   const V3<SF> cam_s(SF(cam.x), SF(cam.y), SF(cam.z));
   V3<float> total(0.0f, 0.0f, 0.0f);
+  V3<SF> total_s(SF(0.0f), SF(0.0f), SF(0.0f));  // STRICT accumulates in the reference's order and arithmetic
+  const V3<SF> light_s(SF(light.x), SF(light.y), SF(light.z));
   const int rays = A * A;
   // Rays of a pixel are processed in groups of kGroup, in the reference's order dy*A + dx
   // (kernels.cl:393-397).  Phase 1 finds the primary hit of each ray of the group and parks it in this
@@ -245,21 +249,59 @@ __global__ void __launch_bounds__(kThreads, RT_MINBLOCKS) draw_fast_kernel(const
       hit.color = make_float4(0.0f, 0.0f, 0.0f, 1.0f);
       if (hit.id >= 0) hit.color = sc.g.tcol[hit.id];
       else if (hit.id <= -2) hit.color = c_sphere_color[-2 - hit.id];
-      V3<float> dir(0.0f, 0.0f, 0.0f);
+      V3<SF> dir_s(SF(0.0f), SF(0.0f), SF(0.0f));
       if (hit.id != -1 && hit.color.w <= 0.0f) {
         // mirror / glass: the bounce needs the ray direction again (same strict sequence as phase 1)
         const int idx = first_dy * A + first_dx + k;
         const int ddy = idx / A, ddx = idx - ddy * A;
         const V3<SF> d0 = base + V3<SF>(SF((float)ddx), SF((float)ddy), SF(0.0f));
-        const V3<SF> dns = normalize(V3<SF>(dot(r0, d0), dot(r1, d0), dot(r2, d0)));
-        dir = V3<float>(dns.x.v, dns.y.v, dns.z.v);
+        dir_s = normalize(V3<SF>(dot(r0, d0), dot(r1, d0), dot(r2, d0)));
       }
       sc.clist = warp_list;
       sc.n_clist = n_warp_list;
       // direct light of a diffuse hit, or secondary_light's bounce loop (kernels.cl:342-365) ending in
       // the same shading — a single call site for both
-      float medium = RT_AIR, gain = 1.0f;
+      float medium = RT_AIR;
       int bounce = 0;
+      if constexpr (STRICT) {
+        HitRec<SF> hs;
+        hs.id = hit.id;
+        hs.point = V3<SF>(SF(hit.point.x), SF(hit.point.y), SF(hit.point.z));
+        hs.normal = V3<SF>(SF(hit.normal.x), SF(hit.normal.y), SF(hit.normal.z));
+        hs.color = hit.color;
+        bool bounced = false;
+        while (hs.id != -1) {
+          if (hs.color.w > 0.0f) {
+            if (SINGLE && !have_jit) {
+              uint32_t rx, ry, rz;
+              seed_rng(global_id, rx, ry, rz);
+              Jitters<CH> jr;
+              make_jitters<CH, true>(rx, ry, rz, jr);
+              jit.store(jr);
+              have_jit = true;
+            }
+            const SF dl = direct_light_strict<CH, SINGLE, JittersShared<CH, kThreads>>(sc, hs.point, hs.normal, light_s, S, global_id, jit);
+            const V3<SF> lightv(SF(RT_INDIRECT) + dl, SF(RT_INDIRECT) + dl, SF(RT_INDIRECT) + dl);
+            // primary: colour*(indirect + direct) (kernels.cl:422); after a bounce: 0.9*light*colour (:355)
+            total_s = total_s + (bounced ? scale(SF(0.9f), lightv) * xyz<SF>(hs.color) : xyz<SF>(hs.color) * lightv);
+            break;
+          }
+          if (bounce >= p.B) break;
+          bounce++;
+          V3<SF> start, ndir;
+          if (hs.color.w == 0.0f) reflect_ray<SF>(dir_s, hs.normal, hs.point, start, ndir, medium);
+          else refract_ray<SF>(dir_s, hs.normal, hs.point, medium, start, ndir, medium);
+          dir_s = ndir;
+          hs.id = -1;
+          hs.color.w = 1.0f;
+          closest_hit<SF>(sc.g, start, dir_s, hs);
+          bounced = true;
+          sc.clist = full_list;  // the warp list was built for the primary hits only
+          sc.n_clist = n_sh;
+        }
+      } else {
+      V3<float> dir(dir_s.x.v, dir_s.y.v, dir_s.z.v);
+      float gain = 1.0f;
       while (hit.id != -1) {
         if (hit.color.w > 0.0f) {
           if (SINGLE && !have_jit) {
@@ -287,7 +329,13 @@ __global__ void __launch_bounds__(kThreads, RT_MINBLOCKS) draw_fast_kernel(const
         sc.clist = full_list;  // the warp list was built for the primary hits only
         sc.n_clist = n_sh;
       }
+      }
     }
+  }
+  if constexpr (STRICT) {
+    const SF fa = SF(__int2float_rn(A * A));
+    p.out[(size_t)y * p.W + x] = pack_argb<SF>(V3<SF>(div_(total_s.x, fa), div_(total_s.y, fa), div_(total_s.z, fa)));
+    return;
   }
   const float ia = 1.0f / (float)(A * A);
   p.out[(size_t)y * p.W + x] = pack_argb<float>(V3<float>(total.x * ia, total.y * ia, total.z * ia));
@@ -299,8 +347,12 @@ __global__ void __launch_bounds__(kThreads, RT_MINBLOCKS) draw_fast_kernel(const
 cudaError_t RT_CAT(launch_fast_ch, RT_FAST_CH)(rt_ctx *ctx, const FrameParams &fp, cudaStream_t stream) {
   constexpr int CH = RT_FAST_CH;
   ctx->launch_extra_smem = sizeof(float) * (3 * CH + 4 * 7) * kThreads;  // jitter columns + parked primary hits
-  if (fp.S == CH) return launch_kernel(draw_fast_kernel<CH, true>, ctx, fp, stream);
-  return launch_kernel(draw_fast_kernel<CH, false>, ctx, fp, stream);
+  if (ctx->cfg.flags & RT_FLAG_STRICT_IEEE) {
+    if (fp.S == CH) return launch_kernel(draw_fast_kernel<CH, true, true>, ctx, fp, stream);
+    return launch_kernel(draw_fast_kernel<CH, false, true>, ctx, fp, stream);
+  }
+  if (fp.S == CH) return launch_kernel(draw_fast_kernel<CH, true, false>, ctx, fp, stream);
+  return launch_kernel(draw_fast_kernel<CH, false, false>, ctx, fp, stream);
 }
 
 }  // namespace rt

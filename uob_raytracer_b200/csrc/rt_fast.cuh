@@ -37,6 +37,8 @@
 //  * The mirror sphere's shadow test is skipped per point when the whole cone of
 //    jittered rays misses the sphere.
 #pragma once
+#include <type_traits>
+
 #include "rt_brute.cuh"
 
 namespace rt {
@@ -233,16 +235,17 @@ __device__ __forceinline__ void seed_rng(int global_id, uint32_t &rx, uint32_t &
   rz = xorshift32(__float2uint_rz(__fmul_rn(__int2float_rn(global_id), 19.0f)));
 }
 
-template <int CH>
+template <int CH, bool STRICT = false>
 __device__ __forceinline__ void make_jitters(uint32_t &rx, uint32_t &ry, uint32_t &rz, Jitters<CH> &j) {
+  typedef typename std::conditional<STRICT, sfloat, float>::type T;  // STRICT: crush's own operation sequence
 #pragma unroll
   for (int k = 0; k < CH; k++) {
     rx = xorshift32(rx);
     ry = xorshift32(ry);
     rz = xorshift32(rz);
-    j.x[k] = crush1<float>(rx, RT_LIGHT_SPREAD);
-    j.y[k] = crush1<float>(ry, RT_LIGHT_SPREAD);
-    j.z[k] = crush1<float>(rz, RT_LIGHT_SPREAD);
+    j.x[k] = raw(crush1<T>(rx, RT_LIGHT_SPREAD));
+    j.y[k] = raw(crush1<T>(ry, RT_LIGHT_SPREAD));
+    j.z[k] = raw(crush1<T>(rz, RT_LIGHT_SPREAD));
   }
 }
 
@@ -368,6 +371,148 @@ __device__ __forceinline__ float direct_light_fast(const FastScene &sc, V3<float
     }
   }
   return (float)lit * lam * rcp_approx(4.0f * RT_PI_F * radius_sq * (float)S);
+}
+
+// ---------------------------------------------------------------------------------------------
+// RT_FLAG_STRICT_IEEE over the same culls.  The culls are conservative — they only skip (point,
+// triangle) pairs in which no sample can pass the reference's tests, with margins (kJitterMax,
+// kSlack) orders of magnitude above float rounding — so evaluating the surviving pairs with the
+// reference's exact operation sequence gives the same occlusion mask, hence the same frame bit for
+// bit, as the un-culled strict kernel (tests compare the two and both with the reference frames).
+// ---------------------------------------------------------------------------------------------
+template <int CH, class J>
+__device__ __forceinline__ unsigned shadow_occ_strict(const FastScene &sc, V3<sfloat> start_s, V3<sfloat> r_s, sfloat radius_sq_s,
+                                                      const J &j, unsigned valid_mask) {
+  typedef sfloat T;
+  constexpr unsigned FULL = (CH >= 32) ? 0xffffffffu : ((1u << CH) - 1u);
+  unsigned occ = ~valid_mask & FULL;  // padding samples of a ragged chunk: never evaluated, ignored by the caller
+  const V3<float> start(start_s.x.v, start_s.y.v, start_s.z.v), r(r_s.x.v, r_s.y.v, r_s.z.v);
+  const float radius_sq = radius_sq_s.v;
+  const float R = sqrt_approx(radius_sq);
+  const float inv_r2 = rcp_approx(radius_sq);
+  const float kk = (R > 2.0f * kJitterMax) ? kSlack * R * rcp_approx(R - kJitterMax) : 1e30f;
+  for (int l = 0; l < sc.n_clist; l++) {
+    const float4 *q = sc.shad + 4 * sc.clist[l];
+    const float4 Q0 = q[0], Q1 = q[1];
+    {  // the two culls of shadow_lit_count, in fast float arithmetic
+      const V3<float> b(start.x - Q0.x, start.y - Q0.y, start.z - Q0.z);
+      const float c0 = Q1.x, c1 = Q1.y, c2 = Q1.z;
+      const float num = (b.x * c0 - b.y * c1) + b.z * c2;
+      const float rN = (r.x * c0 - r.y * c1) + r.z * c2;
+      const float w = xor_sign(rN, __float_as_uint(num) & 0x80000000u);
+      // |num| at rounding level: its sign (which selects the side of the cull) is not trustworthy — evaluate
+      const bool num_ok = fabsf(num) > 1e-5f * (fabsf(b.x * c0) + fabsf(b.y * c1) + fabsf(b.z * c2));
+      if (num_ok && fabsf(num) >= (Q0.w - w) * kk) continue;
+      const float arN = fabsf(rN);
+      if (arN > Q0.w) {
+        const float4 Q2 = q[2], Q3 = q[3];
+        const V3<float> e1(Q2.x, Q2.y, Q2.z), e2(Q3.x, Q3.y, Q3.z);
+        const V3<float> U(b.y * e2.z - b.z * e2.y, b.z * e2.x - b.x * e2.z, b.x * e2.y - b.y * e2.x);
+        const V3<float> V(e1.y * b.z - e1.z * b.y, e1.z * b.x - e1.x * b.z, e1.x * b.y - e1.y * b.x);
+        const float lb = sqrt_approx(dot(b, b));
+        const float mU = lb * Q3.w, mV = lb * Q2.w;
+        const unsigned sg = __float_as_uint(rN) & 0x80000000u;
+        const float eu = xor_sign(dot(r, U), sg), ev = xor_sign(dot(r, V), sg);
+        if ((eu < -mU) | (ev < -mV) | ((eu + ev) - (mU + mV) > arN + Q0.w)) continue;
+      }
+    }
+    // in_shadow's per-triangle sequence (kernels.cl:246-276), as shadow_pair<sfloat>
+    const float4 Q2 = q[2], Q3 = q[3];
+    const V3<T> v0(T(Q0.x), T(Q0.y), T(Q0.z)), e1(T(Q2.x), T(Q2.y), T(Q2.z)), e2(T(Q3.x), T(Q3.y), T(Q3.z));
+    const T c0 = T(Q1.x), c1 = T(Q1.y), c2 = T(Q1.z);
+    const V3<T> b = start_s - v0;
+    const T detA0 = (b.x * c0 - b.y * c1) + b.z * c2;
+    const T U0 = b.y * e2.z - b.z * e2.y, U1 = b.x * e2.z - b.z * e2.x, U2 = b.x * e2.y - b.y * e2.x;
+    const T V0 = e1.y * b.z - e1.z * b.y, V1 = e1.x * b.z - e1.z * b.x, V2 = e1.x * b.y - e1.y * b.x;
+#pragma unroll
+    for (int k = 0; k < CH; k++) {
+      if ((occ >> k) & 1u) continue;
+      const V3<T> d = r_s + V3<T>(T(j.jx(k)), T(j.jy(k)), T(j.jz(k)));
+      const V3<T> nd = -d;
+      const T detA = (nd.x * c0 - nd.y * c1) + nd.z * c2;
+      const T inv = rcp_(detA);
+      const T t = detA0 * inv;
+      const V3<T> dv = scale(t, d);
+      const T dist = dv.x * dv.x + dv.y * dv.y + dv.z * dv.z;
+      if (t >= T(0.0f) && dist < radius_sq_s) {
+        const T u = ((nd.x * U0 - nd.y * U1) + nd.z * U2) * inv;
+        const T v = ((nd.x * V0 - nd.y * V1) + nd.z * V2) * inv;
+        if (u >= T(0.0f) && v >= T(0.0f) && (u + v) <= T(1.0f)) occ |= 1u << k;
+      }
+    }
+    if (occ == FULL) return occ;
+  }
+#pragma unroll
+  for (int i = 0; i < RT_SPHERES; i++) {
+    if (c_sphere_color[i].w == -1.0f) continue;  // glass casts no shadow (kernels.cl:279)
+    const float4 cr = c_sphere_center_r2[i];
+    {  // cone cull of shadow_lit_count
+      const V3<float> L(start.x - cr.x, start.y - cr.y, start.z - cr.z);
+      const float LL = dot(L, L);
+      const float Lr = dot(L, r);
+      const float perp2 = LL - Lr * Lr * inv_r2;
+      const float lim = kSlack * sqrt_approx(cr.w) + sqrt_approx(LL) * (kk * kJitterMax * rcp_approx(R));
+      if (perp2 > lim * lim) continue;
+    }
+    const V3<T> L = start_s - xyz<T>(cr);
+    const T c = dot(L, L) - T(cr.w);
+#pragma unroll
+    for (int k = 0; k < CH; k++) {  // kernels.cl:278-307, as shadow_spheres<sfloat>
+      if ((occ >> k) & 1u) continue;
+      const V3<T> d = r_s + V3<T>(T(j.jx(k)), T(j.jy(k)), T(j.jz(k)));
+      const T a = dot(d, d);
+      const T b = T(2.0f) * dot(d, L);
+      const T disc = b * b - T(4.0f) * a * c;
+      if (disc < T(0.0f)) continue;
+      const T sq = sqrt_(disc);
+      const T qq = (b > T(0.0f)) ? T(-0.5f) * (b + sq) : T(-0.5f) * (b - sq);
+      const T x0 = div_(qq, a);
+      const T x1 = div_(c, qq);
+      const T x_min = cl_min(x0, x1);
+      const T x_max = cl_max(x0, x1);
+      const V3<T> min_dir = scale(x_min, d);
+      const V3<T> max_dir = scale(x_max, d);
+      const T min_dist = dot(min_dir, min_dir);
+      const T max_dist = dot(max_dir, max_dir);
+      if ((x_min >= T(0.0f) && min_dist < radius_sq_s) || (x_max >= T(0.0f) && max_dist < radius_sq_s)) occ |= 1u << k;
+    }
+  }
+  return occ;
+}
+
+// direct_light (kernels.cl:313-340) in the reference's operation sequence (cf. direct_light<sfloat> in rt_brute.cuh);
+// the jitters come from the pixel's shared-memory column (SINGLE) or are regenerated per chunk.
+template <int CH, bool SINGLE, class J>
+__device__ __forceinline__ sfloat direct_light_strict(const FastScene &sc, V3<sfloat> point, V3<sfloat> normal, V3<sfloat> light_pos, int S,
+                                                      int global_id, const J &jit) {
+  typedef sfloat T;
+  const V3<T> dir = light_pos - point;
+  const V3<T> start = point + scale(T(RT_BIAS), dir);
+  const T radius_sq = (dir.x * dir.x + dir.y * dir.y) + dir.z * dir.z;
+  const T lam = T(RT_LIGHT_COLOR) * cl_max(dot(dir, normal), T(0.0f));
+  const T den = T(4.0f) * T(RT_PI_F) * radius_sq;
+  // mask * lam / den for mask = 1 and mask = 0 (kernels.cl:334-336): the two possible per-sample terms
+  const T term_lit = div_(T(1.0f) * lam, den), term_occ = div_(T(0.0f) * lam, den);
+  T total = T(0.0f);
+  if constexpr (SINGLE) {
+    const unsigned occ = shadow_occ_strict<CH, J>(sc, start, dir, radius_sq, jit, 0xffffffffu);
+#pragma unroll
+    for (int k = 0; k < CH; k++) total = total + (((occ >> k) & 1u) ? term_occ : term_lit);
+  } else {
+    uint32_t rx, ry, rz;
+    seed_rng(global_id, rx, ry, rz);
+#pragma unroll 1
+    for (int s0 = 0; s0 < S; s0 += CH) {
+      Jitters<CH> jj;
+      make_jitters<CH, true>(rx, ry, rz, jj);
+      const unsigned valid = (s0 + CH > S) ? ((1u << (S - s0)) - 1u) : 0xffffffffu;
+      const unsigned occ = shadow_occ_strict<CH, Jitters<CH>>(sc, start, dir, radius_sq, jj, valid);
+#pragma unroll
+      for (int k = 0; k < CH; k++)
+        if (s0 + k < S) total = total + (((occ >> k) & 1u) ? term_occ : term_lit);
+    }
+  }
+  return div_(total, T(__int2float_rn(S)));
 }
 
 }  // namespace rt
