@@ -309,6 +309,7 @@ __device__ __forceinline__ void shadow_spheres(V3<T> start, const ShadowRays<T, 
 //   shadow(start, rays, r, radius_sq)  kernels.cl:243-311 for CH rays sharing an origin -> occlusion mask
 // ---------------------------------------------------------------------------
 template <class T> struct BruteTracer {
+  static constexpr bool kSkipUnlit = false;  // the reference's plain loops: trace every shadow ray
   SceneView sc;
   __device__ __forceinline__ BruteTracer<sfloat> strict() const {  // same scene, reference arithmetic
     BruteTracer<sfloat> t;
@@ -367,6 +368,11 @@ __device__ __forceinline__ V3<T> direct_light(const Tracer &tr, V3<T> point, V3<
   const T radius_sq = (dir.x * dir.x + dir.y * dir.y) + dir.z * dir.z;
   const T lam = T(RT_LIGHT_COLOR) * cl_max(dot(dir, normal), T(0.0f));
   const T den = T(4.0f) * T(RT_PI_F) * radius_sq;
+  if constexpr (Tracer::kSkipUnlit) {
+    // a point that faces away from the light: every term mask*lam/den is exactly +0 whatever the shadow rays
+    // find (kernels.cl:334-336), so they need not be traced
+    if (raw(lam) == 0.0f && raw(den) > 0.0f && raw(den) < 3.0e38f) return V3<T>(T(0.0f), T(0.0f), T(0.0f));
+  }
   T total = T(0.0f);
   [[maybe_unused]] int lit = 0;
   for (int s0 = 0; s0 < S; s0 += CH) {

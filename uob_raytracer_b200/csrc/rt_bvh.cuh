@@ -65,6 +65,7 @@ struct BvhBigPrimary {
 };
 
 template <class T> struct BvhTracer {
+  static constexpr bool kSkipUnlit = true;  // direct_light: no shadow rays for points facing away from the light
   BvhView bv;
   BvhBigPrimary big{nullptr, nullptr, 0, -1};
   __device__ __forceinline__ BvhTracer<sfloat> strict() const {  // same tree, reference arithmetic

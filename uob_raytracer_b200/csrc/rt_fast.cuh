@@ -356,6 +356,8 @@ __device__ __forceinline__ float direct_light_fast(const FastScene &sc, V3<float
   const V3<float> start = point + scale(RT_BIAS, r);
   const float radius_sq = (r.x * r.x + r.y * r.y) + r.z * r.z;
   const float lam = RT_LIGHT_COLOR * fmaxf(dot(r, normal), 0.0f);
+  // facing away from the light: the result is lit*0/den = 0 whatever the shadow rays find
+  if (lam == 0.0f && radius_sq > 0.0f && radius_sq < 1.0e37f) return 0.0f;
   int lit = 0;
   if constexpr (SINGLE) {
     lit = shadow_lit_count<CH, J>(sc, start, r, radius_sq, jit, 0xffffffffu);
@@ -491,6 +493,8 @@ __device__ __forceinline__ sfloat direct_light_strict(const FastScene &sc, V3<sf
   const T radius_sq = (dir.x * dir.x + dir.y * dir.y) + dir.z * dir.z;
   const T lam = T(RT_LIGHT_COLOR) * cl_max(dot(dir, normal), T(0.0f));
   const T den = T(4.0f) * T(RT_PI_F) * radius_sq;
+  // facing away from the light: every term mask*lam/den is exactly +0, and so is the sum and total/S
+  if (lam.v == 0.0f && den.v > 0.0f && den.v < 3.0e38f) return T(0.0f);
   // mask * lam / den for mask = 1 and mask = 0 (kernels.cl:334-336): the two possible per-sample terms
   const T term_lit = div_(T(1.0f) * lam, den), term_occ = div_(T(0.0f) * lam, den);
   T total = T(0.0f);
