@@ -156,7 +156,7 @@ def gpu_ray_counts(cfg, scene, rot, cam4, light4, device=0, row0=0, rows=0) -> d
         return r.ray_counts()
 
 
-def cpu_reference_frame(cfg, rows_step: int, threads: int = 0):
+def cpu_reference_frame(cfg, rows_step: int, threads: int = 0, speed: bool = False):
     """One (possibly row-subsampled) frame by the reference's own kernel on host threads.
     Returns (seconds, rays traced, kind)."""
     from oracle import bind as ob
@@ -185,7 +185,7 @@ def cpu_reference_frame(cfg, rows_step: int, threads: int = 0):
     if ob.ref_available(cfg.aa, cfg.shadow_samples, cfg.max_bounces):
         kind = "reference"
         ob.ref_render(cfg.width, cfg.height, cfg.aa, cfg.shadow_samples, cfg.max_bounces, cfg.focal, scene.verts,
-                      scene.normals, scene.colors, rot, cam4, light4, row_step=rows_step, threads=threads)
+                      scene.normals, scene.colors, rot, cam4, light4, row_step=rows_step, threads=threads, speed=speed)
     else:
         kind = "port"
         ob.oracle_render(cfg.width, cfg.height, cfg.aa, cfg.shadow_samples, cfg.max_bounces, cfg.focal, scene.verts,
@@ -527,6 +527,15 @@ def run_ours(args, cfg) -> int:
                           f", best of {i + 1} frames; verbatim kernels.cl via g++ shim (-O2, strict IEEE), all host threads",
                 "ms_per_frame": None if mesh else round(best * step * 1e3, 1)}
             if not mesh:
+                try:  # the optimiser-let-loose build of the same text, reported separately (not bit-reproducible)
+                    from oracle import bind as ob
+                    if ob.ref_speed_available(cfg.aa, cfg.shadow_samples, cfg.max_bounces):
+                        tb = min(cpu_reference_frame(cfg, step, speed=True)[0] for _ in range(3))
+                        line["cpu_baseline"]["speed_build"] = {"value": round(rays / tb / 1e6, 2), "unit": UNIT,
+                                                               "flags": "-O3 -march=x86-64-v3 -ffp-contract=fast",
+                                                               "ms_per_frame": round(tb * step * 1e3, 1)}
+                except Exception as e:  # noqa: BLE001
+                    line["cpu_baseline"]["speed_build"] = {"unavailable": str(e)[:200]}
                 # Same-box GPU yardstick, still the baseline leg: the reference's own OpenCL kernel on THIS B200 through
                 # NVIDIA's OpenCL driver (oracle/ref_ocl.c; parameter tokens substituted for cfg != HEAD).  Reported, never used.
                 try:

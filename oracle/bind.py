@@ -181,10 +181,24 @@ def _ref(name: str) -> ctypes.CDLL:
     return _ref_cache[name]
 
 
+def ref_speed_available(aa, shadow_samples, max_bounces) -> bool:
+    """The -O3 x86-64-v3 build of the reference kernel exists and this CPU can run it (AVX2 + FMA)."""
+    if not os.path.exists(os.path.join(REF_DIR, f"libref_a{aa}_s{shadow_samples}_b{max_bounces}_speed.so")):
+        return False
+    try:
+        with open("/proc/cpuinfo") as f:
+            flags = next((line for line in f if line.startswith("flags")), "")
+    except OSError:
+        return False
+    return all(f" {w}" in flags for w in ("avx2", "fma", "bmi2"))
+
+
 def ref_render(W, H, aa, shadow_samples, max_bounces, focal, verts, normals, colors, rot12, cam, light,
-               y0=0, y1=None, row_step=1, threads=0) -> np.ndarray:
-    """The verbatim kernels.cl `draw` on host threads. Returns uint32[H,W]."""
-    lib = _ref(f"libref_a{aa}_s{shadow_samples}_b{max_bounces}.so")
+               y0=0, y1=None, row_step=1, threads=0, speed=False) -> np.ndarray:
+    """The verbatim kernels.cl `draw` on host threads. Returns uint32[H,W].  speed=True: the -O3/AVX2/FMA build
+    (timing only, not bit-reproducible)."""
+    suffix = "_speed" if speed else ""
+    lib = _ref(f"libref_a{aa}_s{shadow_samples}_b{max_bounces}{suffix}.so")
     lib.ref_render.argtypes = [ctypes.c_int] * 5 + [_fp, _fp, _fp, ctypes.c_int, _fp, _fp, _fp, ctypes.c_float, _u32p,
                                                     ctypes.c_int]
     verts, normals, colors = _f32(verts, (-1, 4)), _f32(normals, (-1, 4)), _f32(colors, (-1, 4))
