@@ -251,317 +251,350 @@ def run_ours(args, cfg) -> int:
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
-    W, H = cfg.width, cfg.height
-    from uob_raytracer_b200 import tiles
-    row0, rows = tiles.row_tile(H, world, rank)
-    scene, rot, cam4, light4 = scene_and_camera(cfg.name)
-    if cfg.name == "cfg4":
-        counts = gpu_ray_counts(cfg, scene, rot, cam4, light4, device=local_rank)
-        rays_source = "strict-kernel ray counters (RT_FLAG_COUNT_RAYS; equal to the oracle's on cfg1/cfg2 — the oracle cannot run 1.3 M triangles)"
-    else:
-        counts = load_counts(cfg.name)
-        rays_source = "oracle counters (tests/golden/ray_counts.json)"
+    # The north star quotes 1080p AND 4K at every GPU count: a default cfg2 run first takes a short measurement of
+    # cfg3 (4K, 16 spp) with the same partition and gather and reports it as "also_4k" in the same JSON line.
+    main_cfg = cfg
+    also_4k = None
+    passes = [(main_cfg, True)]
+    if main_cfg.name == "cfg2" and not args.no_4k and not args.strict:
+        passes.insert(0, (u.CONFIGS["cfg3"], False))
+    for cfg, primary in passes:
+        steps = args.steps if primary else max(5, min(args.steps, 20))
+        W, H = cfg.width, cfg.height
+        from uob_raytracer_b200 import tiles
+        row0, rows = tiles.row_tile(H, world, rank)
+        scene, rot, cam4, light4 = scene_and_camera(cfg.name)
+        if cfg.name == "cfg4":
+            counts = gpu_ray_counts(cfg, scene, rot, cam4, light4, device=local_rank)
+            rays_source = "strict-kernel ray counters (RT_FLAG_COUNT_RAYS; equal to the oracle's on cfg1/cfg2 — the oracle cannot run 1.3 M triangles)"
+        else:
+            counts = load_counts(cfg.name)
+            rays_source = "oracle counters (tests/golden/ray_counts.json)"
 
-    # Multi-GPU gather of the frame on rank 0:
-    #   nccl: contiguous row tiles, in-place NCCL all-gather into every rank's frame (the north-star path)
-    #   p2p : 16x16 blocks interleaved over the ranks (near-perfect balance), every rank's draw kernel
-    #         stores its pixels straight into rank 0's frame over NVLink (CUDA IPC mapping); the hand-over is
-    #         a pair of flags in rank 0's memory (rt_peer_signal / rt_peer_wait: release store after a
-    #         system fence, acquire spin) — no collective at all
-    #   p2p-nccl: the same stores, ordered by a 4-byte NCCL all-reduce instead of the flags
-    gather = args.gather if world > 1 else "none"
-    if gather == "auto":
-        gather = "p2p"
-    stream = torch.cuda.Stream(device=local_rank)  # a real (non-default) stream: the C ABI launches on it
-    torch.cuda.set_stream(stream)
-    sptr = stream.cuda_stream
-    assert sptr != 0
-    frame = torch.zeros(H * W, dtype=torch.int32, device=f"cuda:{local_rank}")
-    tile = frame[row0 * W:(row0 + rows) * W]
-    host = torch.empty(H * W, dtype=torch.int32).pin_memory()
-    flush = torch.empty(256 << 20, dtype=torch.uint8, device=f"cuda:{local_rank}")  # > 126 MB L2
-    token = torch.zeros(1, dtype=torch.int32, device=f"cuda:{local_rank}")
-    peer_ptr = 0
-    fno = [0]  # frame number, the value the hand-over flags count up to
-    r = None
-    if gather in ("p2p", "p2p-nccl"):
-        r = u.Renderer(W, H, cfg.aa, cfg.shadow_samples, cfg.max_bounces, device=local_rank, block_stride=world,
-                       block_phase=rank, strict=args.strict)
-        handle = [r.ipc_export_frame() if rank == 0 else None]
-        dist.broadcast_object_list(handle, src=0)
-        ok = torch.ones(1, dtype=torch.int32, device=f"cuda:{local_rank}")
-        try:
-            target = r.device_frame_ptr if rank == 0 else r.ipc_open_frame(handle[0])
-            peer_ptr = 0 if rank == 0 else target
-        except u.RtError as exc:  # CUDA IPC not available between these processes
-            print(f"bench.py: rank {rank}: {exc}; falling back to --gather nccl", file=sys.stderr)
-            ok.zero_()
-        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
-        if int(ok.item()) == 0:
+        # Multi-GPU gather of the frame on rank 0:
+        #   nccl: contiguous row tiles, in-place NCCL all-gather into every rank's frame (the north-star path)
+        #   p2p : 16x16 blocks interleaved over the ranks (near-perfect balance), every rank's draw kernel
+        #         stores its pixels straight into rank 0's frame over NVLink (CUDA IPC mapping); the hand-over is
+        #         a pair of flags in rank 0's memory (rt_peer_signal / rt_peer_wait: release store after a
+        #         system fence, acquire spin) — no collective at all
+        #   p2p-nccl: the same stores, ordered by a 4-byte NCCL all-reduce instead of the flags
+        gather = args.gather if world > 1 else "none"
+        if gather == "auto":
+            gather = "p2p"
+        stream = torch.cuda.Stream(device=local_rank)  # a real (non-default) stream: the C ABI launches on it
+        torch.cuda.set_stream(stream)
+        sptr = stream.cuda_stream
+        assert sptr != 0
+        frame = torch.zeros(H * W, dtype=torch.int32, device=f"cuda:{local_rank}")
+        tile = frame[row0 * W:(row0 + rows) * W]
+        host = torch.empty(H * W, dtype=torch.int32).pin_memory()
+        flush = torch.empty(256 << 20, dtype=torch.uint8, device=f"cuda:{local_rank}")  # > 126 MB L2
+        token = torch.zeros(1, dtype=torch.int32, device=f"cuda:{local_rank}")
+        peer_ptr = 0
+        fno = [0]  # frame number, the value the hand-over flags count up to
+        r = None
+        if gather in ("p2p", "p2p-nccl"):
+            r = u.Renderer(W, H, cfg.aa, cfg.shadow_samples, cfg.max_bounces, device=local_rank, block_stride=world,
+                           block_phase=rank, strict=args.strict)
+            handle = [r.ipc_export_frame() if rank == 0 else None]
+            dist.broadcast_object_list(handle, src=0)
+            ok = torch.ones(1, dtype=torch.int32, device=f"cuda:{local_rank}")
+            try:
+                target = r.device_frame_ptr if rank == 0 else r.ipc_open_frame(handle[0])
+                peer_ptr = 0 if rank == 0 else target
+            except u.RtError as exc:  # CUDA IPC not available between these processes
+                print(f"bench.py: rank {rank}: {exc}; falling back to --gather nccl", file=sys.stderr)
+                ok.zero_()
+            dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+            if int(ok.item()) == 0:
+                if peer_ptr:
+                    r.ipc_close_frame(peer_ptr)
+                    peer_ptr = 0
+                r.close()
+                r = None
+                gather = "nccl"
+        if r is None:
+            r = u.Renderer(W, H, cfg.aa, cfg.shadow_samples, cfg.max_bounces, device=local_rank, row0=row0, rows=rows,
+                           strict=args.strict)
+            target = frame.data_ptr()
+        r.upload_scene(scene)
+        r.set_stream(sptr)
+
+        flags = target + 4 * W * H  # rank 0's hand-over flags: [r] = rank r finished frame f, [32] = rank 0 consumed frame f
+        consumed_flag = flags + 4 * 32
+
+        def render_only():
+            fno[0] += 1
+            if gather == "p2p" and rank != 0:
+                r.peer_wait(consumed_flag, 1, fno[0] - 1, sptr)  # rank 0 is done with the previous frame
+            r.render_device(rot, cam4, light4, cfg.focal, dev_ptr=target, stream=sptr)
+
+        def gather_only(consume=True):
+            if gather == "nccl":
+                dist.all_gather_into_tensor(frame, tile)
+            elif gather == "p2p-nccl":
+                dist.all_reduce(token)  # orders rank 0's next use of its frame after every peer's stores
+            elif gather == "p2p":
+                if rank == 0:
+                    r.peer_wait(flags + 4, world - 1, fno[0], sptr)
+                    if consume:
+                        r.peer_signal(consumed_flag, fno[0], sptr)
+                else:
+                    r.peer_signal(flags + 4 * rank, fno[0], sptr)
+
+        def step_device():
+            render_only()
+            gather_only()
+
+        fp32_peak = r.measure_fp32_peak() if (rank == 0 and primary) else 0.0
+
+        # sanity (outside every timed region): the gathered frame on rank 0 has every pixel written
+        step_device()
+        torch.cuda.synchronize()
+        if rank == 0:
+            if gather in ("p2p", "p2p-nccl"):
+                r.read_frame_host_ptr(host.data_ptr())
+            else:
+                host.copy_(frame)
+            torch.cuda.synchronize()
+            alpha = (host.numpy().view(np.uint32) >> 24)
+            if not (alpha == 255).all():
+                raise SystemExit(f"bench.py: gathered frame incomplete ({int((alpha != 255).sum())} pixels unwritten)")
+
+        # ---- device-timed throughput ------------------------------------------------
+        for _ in range(max(args.warmup, 3)):
+            step_device()
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+        sampler = ClockSampler(local_rank)
+        if rank == 0:
+            sampler.start()
+        launches0 = r.kernel_launches
+        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+              for _ in range(steps)]
+        torch.cuda.synchronize()
+        t_wall0 = time.perf_counter()
+        for a, k, b in ev:
+            flush.zero_()  # L2 flush between timed iterations; outside the event pair
+            a.record(stream)
+            render_only()
+            k.record(stream)
+            gather_only()
+            b.record(stream)
+        torch.cuda.synchronize()
+        t_wall = time.perf_counter() - t_wall0
+        launches = r.kernel_launches - launches0
+        if dist is not None:
+            dist.barrier()
+        step_ms = [a.elapsed_time(b) for a, _, b in ev]
+        kern_ms = [a.elapsed_time(k) for a, k, _ in ev]
+        total_ms = torch.tensor([sum(step_ms), sum(kern_ms)], dtype=torch.float64, device=f"cuda:{local_rank}")
+        if dist is not None:
+            dist.all_reduce(total_ms, op=dist.ReduceOp.MAX)
+        total_step_ms, total_kern_ms = (float(x) for x in total_ms.cpu())
+        clocks = sampler.stop() if rank == 0 else {}
+
+        if not primary:
+            if rank == 0:
+                ms4 = total_step_ms / steps
+                also_4k = {"workload": cfg.name, "description": cfg.description, "width": W, "height": H, "aa": cfg.aa,
+                           "shadow_samples": cfg.shadow_samples, "max_bounces": cfg.max_bounces, "rays_per_frame": counts["rays"],
+                           "steps": steps, "ms_per_step": round(ms4, 4), "kernel_ms_per_step": round(total_kern_ms / steps, 4),
+                           "value": round(counts["rays"] / ms4 / 1e3, 1), "unit": UNIT, "gather": gather,
+                           "achieved_tflops_algorithmic": round(algorithmic_flops(counts) / (ms4 * 1e-3) / 1e12, 1)}
+            torch.cuda.synchronize()
+            r.synchronize()
+            if dist is not None:
+                dist.barrier()
             if peer_ptr:
                 r.ipc_close_frame(peer_ptr)
-                peer_ptr = 0
+            if dist is not None:
+                dist.barrier()
             r.close()
-            r = None
-            gather = "nccl"
-    if r is None:
-        r = u.Renderer(W, H, cfg.aa, cfg.shadow_samples, cfg.max_bounces, device=local_rank, row0=row0, rows=rows,
-                       strict=args.strict)
-        target = frame.data_ptr()
-    r.upload_scene(scene)
-    r.set_stream(sptr)
+            del frame, host, flush
+            torch.cuda.empty_cache()
+            if dist is not None:
+                dist.barrier()
+            continue
 
-    flags = target + 4 * W * H  # rank 0's hand-over flags: [r] = rank r finished frame f, [32] = rank 0 consumed frame f
-    consumed_flag = flags + 4 * 32
-
-    def render_only():
-        fno[0] += 1
-        if gather == "p2p" and rank != 0:
-            r.peer_wait(consumed_flag, 1, fno[0] - 1, sptr)  # rank 0 is done with the previous frame
-        r.render_device(rot, cam4, light4, cfg.focal, dev_ptr=target, stream=sptr)
-
-    def gather_only(consume=True):
-        if gather == "nccl":
-            dist.all_gather_into_tensor(frame, tile)
-        elif gather == "p2p-nccl":
-            dist.all_reduce(token)  # orders rank 0's next use of its frame after every peer's stores
-        elif gather == "p2p":
-            if rank == 0:
-                r.peer_wait(flags + 4, world - 1, fno[0], sptr)
-                if consume:
-                    r.peer_signal(consumed_flag, fno[0], sptr)
-            else:
-                r.peer_signal(flags + 4 * rank, fno[0], sptr)
-
-    def step_device():
-        render_only()
-        gather_only()
-
-    fp32_peak = r.measure_fp32_peak() if rank == 0 else 0.0
-
-    # sanity (outside every timed region): the gathered frame on rank 0 has every pixel written
-    step_device()
-    torch.cuda.synchronize()
-    if rank == 0:
-        if gather in ("p2p", "p2p-nccl"):
-            r.read_frame_host_ptr(host.data_ptr())
+        # ---- end to end through rt_render (host buffers) ------------------------------
+        e2e_line = None
+        if world == 1:
+            hp = host.data_ptr()
+            for _ in range(3):
+                r.render_host_ptr(rot, cam4, light4, cfg.focal, hp)
+            t0 = time.perf_counter()
+            for _ in range(args.steps):
+                r.render_host_ptr(rot, cam4, light4, cfg.focal, hp)
+            t_e2e = (time.perf_counter() - t0) / args.steps
+            e2e_line = {"value": round(counts["rays"] / t_e2e / 1e6, 1), "unit": UNIT, "ms_per_step": round(t_e2e * 1e3, 4),
+                        "h2d_bytes_per_step": 84, "d2h_bytes_per_step": W * H * 4,
+                        "api": "rt_render (blocking: per-frame args + kernel + read-back into pinned host memory)"}
+            # the same through the pipelined pair rt_render_begin / rt_render_end (a render loop: the read-back of
+            # frame k overlaps the kernel of frame k+1; every frame still lands in host memory)
+            host2 = torch.empty(H * W, dtype=torch.int32).pin_memory()
+            bufs = [hp, host2.data_ptr()]
+            r.render_begin(rot, cam4, light4, cfg.focal, bufs[0])
+            for i in range(1, 4):
+                r.render_begin(rot, cam4, light4, cfg.focal, bufs[i & 1])
+                r.render_end()
+            t0 = time.perf_counter()
+            for i in range(args.steps):
+                r.render_begin(rot, cam4, light4, cfg.focal, bufs[i & 1])
+                r.render_end()
+            t_pipe = (time.perf_counter() - t0) / args.steps
+            r.render_end()
+            e2e_line["pipelined"] = {"value": round(counts["rays"] / t_pipe / 1e6, 1), "unit": UNIT, "ms_per_step": round(t_pipe * 1e3, 4),
+                                     "api": "rt_render_begin / rt_render_end, two frames in flight"}
         else:
-            host.copy_(frame)
-        torch.cuda.synchronize()
-        alpha = (host.numpy().view(np.uint32) >> 24)
-        if not (alpha == 255).all():
-            raise SystemExit(f"bench.py: gathered frame incomplete ({int((alpha != 255).sum())} pixels unwritten)")
+            # every rank: render tile -> all-gather -> rank 0 reads the whole frame back
+            def step_e2e():
+                render_only()
+                gather_only(consume=False)
+                if rank == 0:
+                    if gather in ("p2p", "p2p-nccl"):
+                        r.read_frame_host_ptr(host.data_ptr())  # D2H on the same stream, blocking
+                        if gather == "p2p":
+                            r.peer_signal(consumed_flag, fno[0], sptr)  # the peers may overwrite the frame now
+                    else:
+                        host.copy_(frame, non_blocking=True)
+                torch.cuda.synchronize()
+            for _ in range(3):
+                step_e2e()
+            dist.barrier()
+            t0 = time.perf_counter()
+            for _ in range(args.steps):
+                step_e2e()
+            dist.barrier()
+            t_e2e = torch.tensor([(time.perf_counter() - t0) / args.steps], dtype=torch.float64, device=f"cuda:{local_rank}")
+            dist.all_reduce(t_e2e, op=dist.ReduceOp.MAX)
+            t_e2e = float(t_e2e.cpu())
+            e2e_line = {"value": round(counts["rays"] / t_e2e / 1e6, 1), "unit": UNIT, "ms_per_step": round(t_e2e * 1e3, 4),
+                        "h2d_bytes_per_step": 84, "d2h_bytes_per_step": W * H * 4,
+                        "api": "rt_render_device per rank + " + ("NCCL all-gather" if gather == "nccl" else "peer stores into rank 0's frame + " + ("flag hand-over" if gather == "p2p" else "4-byte all-reduce")) + " + read-back on rank 0"}
 
-    # ---- device-timed throughput ------------------------------------------------
-    for _ in range(max(args.warmup, 3)):
-        step_device()
-    torch.cuda.synchronize()
-    if dist is not None:
-        dist.barrier()
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
-    launches0 = r.kernel_launches
-    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
-          for _ in range(args.steps)]
-    torch.cuda.synchronize()
-    t_wall0 = time.perf_counter()
-    for a, k, b in ev:
-        flush.zero_()  # L2 flush between timed iterations; outside the event pair
-        a.record(stream)
-        render_only()
-        k.record(stream)
-        gather_only()
-        b.record(stream)
-    torch.cuda.synchronize()
-    t_wall = time.perf_counter() - t_wall0
-    launches = r.kernel_launches - launches0
-    if dist is not None:
-        dist.barrier()
-    step_ms = [a.elapsed_time(b) for a, _, b in ev]
-    kern_ms = [a.elapsed_time(k) for a, k, _ in ev]
-    total_ms = torch.tensor([sum(step_ms), sum(kern_ms)], dtype=torch.float64, device=f"cuda:{local_rank}")
-    if dist is not None:
-        dist.all_reduce(total_ms, op=dist.ReduceOp.MAX)
-    total_step_ms, total_kern_ms = (float(x) for x in total_ms.cpu())
-    clocks = sampler.stop() if rank == 0 else {}
-
-    # ---- end to end through rt_render (host buffers) ------------------------------
-    e2e_line = None
-    if world == 1:
-        hp = host.data_ptr()
-        for _ in range(3):
-            r.render_host_ptr(rot, cam4, light4, cfg.focal, hp)
-        t0 = time.perf_counter()
-        for _ in range(args.steps):
-            r.render_host_ptr(rot, cam4, light4, cfg.focal, hp)
-        t_e2e = (time.perf_counter() - t0) / args.steps
-        e2e_line = {"value": round(counts["rays"] / t_e2e / 1e6, 1), "unit": UNIT, "ms_per_step": round(t_e2e * 1e3, 4),
-                    "h2d_bytes_per_step": 84, "d2h_bytes_per_step": W * H * 4,
-                    "api": "rt_render (blocking: per-frame args + kernel + read-back into pinned host memory)"}
-        # the same through the pipelined pair rt_render_begin / rt_render_end (a render loop: the read-back of
-        # frame k overlaps the kernel of frame k+1; every frame still lands in host memory)
-        host2 = torch.empty(H * W, dtype=torch.int32).pin_memory()
-        bufs = [hp, host2.data_ptr()]
-        r.render_begin(rot, cam4, light4, cfg.focal, bufs[0])
-        for i in range(1, 4):
-            r.render_begin(rot, cam4, light4, cfg.focal, bufs[i & 1])
-            r.render_end()
-        t0 = time.perf_counter()
-        for i in range(args.steps):
-            r.render_begin(rot, cam4, light4, cfg.focal, bufs[i & 1])
-            r.render_end()
-        t_pipe = (time.perf_counter() - t0) / args.steps
-        r.render_end()
-        e2e_line["pipelined"] = {"value": round(counts["rays"] / t_pipe / 1e6, 1), "unit": UNIT, "ms_per_step": round(t_pipe * 1e3, 4),
-                                 "api": "rt_render_begin / rt_render_end, two frames in flight"}
-    else:
-        # every rank: render tile -> all-gather -> rank 0 reads the whole frame back
-        def step_e2e():
-            render_only()
-            gather_only(consume=False)
-            if rank == 0:
-                if gather in ("p2p", "p2p-nccl"):
-                    r.read_frame_host_ptr(host.data_ptr())  # D2H on the same stream, blocking
-                    if gather == "p2p":
-                        r.peer_signal(consumed_flag, fno[0], sptr)  # the peers may overwrite the frame now
-                else:
-                    host.copy_(frame, non_blocking=True)
-            torch.cuda.synchronize()
-        for _ in range(3):
-            step_e2e()
-        dist.barrier()
-        t0 = time.perf_counter()
-        for _ in range(args.steps):
-            step_e2e()
-        dist.barrier()
-        t_e2e = torch.tensor([(time.perf_counter() - t0) / args.steps], dtype=torch.float64, device=f"cuda:{local_rank}")
-        dist.all_reduce(t_e2e, op=dist.ReduceOp.MAX)
-        t_e2e = float(t_e2e.cpu())
-        e2e_line = {"value": round(counts["rays"] / t_e2e / 1e6, 1), "unit": UNIT, "ms_per_step": round(t_e2e * 1e3, 4),
-                    "h2d_bytes_per_step": 84, "d2h_bytes_per_step": W * H * 4,
-                    "api": "rt_render_device per rank + " + ("NCCL all-gather" if gather == "nccl" else "peer stores into rank 0's frame + " + ("flag hand-over" if gather == "p2p" else "4-byte all-reduce")) + " + read-back on rank 0"}
-
-    if rank == 0:
-        ms_per_step = total_step_ms / args.steps
-        kern_ms_per_step = total_kern_ms / args.steps
-        mesh = cfg.name == "cfg4"
-        flops = 0.0 if mesh else algorithmic_flops(counts) / world  # per launch (one rank's tile; tiles are near-uniform)
-        achieved = flops / (kern_ms_per_step * 1e-3) / 1e12
-        nominal = 148 * 128 * 2 * 1.965e9 / 1e12
-        line = {
-            "metric": METRIC, "value": round(counts["rays"] / ms_per_step / 1e3, 1), "unit": UNIT, "n_gpus": world,
-            "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": round(ms_per_step, 4),
-            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": cfg.name, "description": cfg.description, "width": W, "height": H, "aa": cfg.aa,
-                       "shadow_samples": cfg.shadow_samples, "max_bounces": cfg.max_bounces, "focal": cfg.focal,
-                       "rays_per_frame": counts["rays"], "rays_source": rays_source, "triangles": scene.n,
-                       "partition": (f"{world} row tile(s) of {rows} rows" + (", in-place NCCL all-gather per frame" if world > 1 else ""))
-                       if gather not in ("p2p", "p2p-nccl") else f"16x16-pixel blocks interleaved over {world} ranks, peer stores into rank 0's frame over NVLink + " + ("release/acquire flag hand-over" if gather == "p2p" else "4-byte all-reduce") + " per frame",
-                       "gather": gather,
-                       "l2": "flushed between timed iterations (256 MiB memset outside the timed event pairs); "
-                             "the scene is 3.4 KB and lives in shared memory",
-                       "arithmetic": ("RT_FLAG_STRICT_IEEE: reference operation sequence, frames bit-identical to the reference's" if args.strict else
-                                      "fast path (FMA, division-free shadow tests), within 1/255 on >= 99.9 % of pixels; "
-                                      "bit_exact_mode = the same frame through RT_FLAG_STRICT_IEEE")},
-            "wall_ms_per_step_incl_flush": round(t_wall / args.steps * 1e3, 4),
-            "kernel_ms_per_step": round(kern_ms_per_step, 4),
-            "e2e": e2e_line,
-            "gpu_launches": int(launches),
-            "clocks": clocks,
-            "roofline": {"bound": "fp32", "kernel": "draw_fast_kernel<%d,true>" % (10 if cfg.shadow_samples % 10 == 0 else 8),
-                         "achieved": round(achieved, 3), "peak": round(fp32_peak, 3), "unit": "TFLOP/s",
-                         "frac": round(achieved / fp32_peak, 4) if fp32_peak else None,
-                         "peak_source": "FFMA microbenchmark in this run (rt_measure_fp32_peak); MEASURED_PEAKS.json has no FP32 entry",
-                         "peak_nominal": round(nominal, 1), "frac_of_nominal": round(achieved / nominal, 4),
-                         "algorithmic_gflop_per_launch": round(flops / 1e9, 3),
-                         "traffic": load_traffic(cfg.name), "ncu": load_ncu(cfg.name),
-                         "note": "achieved = ALGORITHMIC FLOPs of the reference's brute-force algorithm (SURVEY.md 8d) / kernel time; the "
-                                 "kernel executes fewer: conservative culls (tile binning, plane/edge/box culls) skip tests the "
-                                 "reference must perform, so frac can exceed 1.  What bounds the kernel is instruction issue and "
-                                 "latency (see ncu: issue slots and FMA pipe utilisation), not FMA throughput."},
-        }
-        if mesh:
-            # BVH path: no FLOP bound.  Algorithmic bytes: a binary BVH with 4-triangle leaves needs
-            # ceil(log2(N/4)) = 19 node visits x 64 B + 4 triangles x 48 B = 1.4 KB per ray.
-            bytes_per_ray = 19 * 64 + 4 * 48
-            peaks = {}
-            try:
-                with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
-                    peaks = json.load(f)
-            except Exception:
-                pass
-            peak = float(peaks.get("hbm_gbs", 6650.0))
-            ach = bytes_per_ray * counts["rays"] / world / (kern_ms_per_step * 1e-3) / 1e9
-            line["roofline"] = {"bound": "hbm", "kernel": "draw_bvh_kernel<float,8>", "achieved": round(ach, 1), "peak": peak,
-                                "unit": "GB/s", "frac": round(ach / peak, 4),
-                                "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 GB/s (of fallback)",
-                                "algorithmic_bytes_per_ray": bytes_per_ray, "traffic": load_traffic(cfg.name), "ncu": load_ncu(cfg.name),
-                                "note": "nodes 42 MB + triangles 63 MB stay in the 126 MB L2 (ncu: DRAM 0.1 %, L2 0.9 %, L1 22 % of peak): the "
-                                        "traversal is latency / issue-bound inside the SM, the byte figure is only the SURVEY 8d yardstick"}
-        if world == 1 and not args.strict:
-            # the bit-exact path (frames identical to the reference's), same frame, device time
-            with u.Renderer(W, H, cfg.aa, cfg.shadow_samples, cfg.max_bounces, device=local_rank, strict=True) as rs:
-                rs.upload_scene(scene)
-                ms = []
-                for _ in range(8):
-                    rs.render_device(rot, cam4, light4, cfg.focal)
-                    ms.append(rs.last_kernel_ms)
-                best = min(ms[3:])
-            line["bit_exact_mode"] = {"flag": "RT_FLAG_STRICT_IEEE", "kernel_ms_per_step": round(best, 4),
-                                      "value": round(counts["rays"] / best / 1e3, 2), "unit": UNIT,
-                                      "note": "same culls, surviving tests and all shading in the reference's IEEE operation sequence"}
-        # CPU baseline on this box's host cores (N = 1 only)
-        if world == 1 and not args.no_cpu_baseline:
-            step = pick_row_step(cfg)
-            best, rays, kind = None, 0, "reference"
-            t_budget = time.perf_counter()
-            for i in range(1 if mesh else 6):
-                t, rays, kind = cpu_reference_frame(cfg, step)
-                best = t if best is None else min(best, t)
-                if time.perf_counter() - t_budget > 15.0:
-                    break
-            line["cpu_baseline"] = {
-                "value": round(rays / best / 1e6, 2), "unit": UNIT, "cores": os.cpu_count(), "kind": kind,
-                "sample": ("cfg4 scene at 480x270, one row through the mesh" if mesh else f"{cfg.name}, " + ("all rows" if step == 1 else f"every {step}th row")) +
-                          f", best of {i + 1} frames; verbatim kernels.cl via g++ shim (-O2, strict IEEE), all host threads",
-                "ms_per_frame": None if mesh else round(best * step * 1e3, 1)}
-            if not mesh:
-                try:  # the optimiser-let-loose build of the same text, reported separately (not bit-reproducible)
-                    from oracle import bind as ob
-                    if ob.ref_speed_available(cfg.aa, cfg.shadow_samples, cfg.max_bounces):
-                        tb = min(cpu_reference_frame(cfg, step, speed=True)[0] for _ in range(3))
-                        line["cpu_baseline"]["speed_build"] = {"value": round(rays / tb / 1e6, 2), "unit": UNIT,
-                                                               "flags": "-O3 -march=x86-64-v3 -ffp-contract=fast",
-                                                               "ms_per_frame": round(tb * step * 1e3, 1)}
-                except Exception as e:  # noqa: BLE001
-                    line["cpu_baseline"]["speed_build"] = {"unavailable": str(e)[:200]}
-                # Same-box GPU yardstick, still the baseline leg: the reference's own OpenCL kernel on THIS B200 through
-                # NVIDIA's OpenCL driver (oracle/ref_ocl.c; parameter tokens substituted for cfg != HEAD).  Reported, never used.
+        if rank == 0:
+            ms_per_step = total_step_ms / args.steps
+            kern_ms_per_step = total_kern_ms / args.steps
+            mesh = cfg.name == "cfg4"
+            flops = 0.0 if mesh else algorithmic_flops(counts) / world  # per launch (one rank's tile; tiles are near-uniform)
+            achieved = flops / (kern_ms_per_step * 1e-3) / 1e12
+            nominal = 148 * 128 * 2 * 1.965e9 / 1e12
+            line = {
+                "metric": METRIC, "value": round(counts["rays"] / ms_per_step / 1e3, 1), "unit": UNIT, "n_gpus": world,
+                "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": round(ms_per_step, 4),
+                "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "config": {"workload": cfg.name, "description": cfg.description, "width": W, "height": H, "aa": cfg.aa,
+                           "shadow_samples": cfg.shadow_samples, "max_bounces": cfg.max_bounces, "focal": cfg.focal,
+                           "rays_per_frame": counts["rays"], "rays_source": rays_source, "triangles": scene.n,
+                           "partition": (f"{world} row tile(s) of {rows} rows" + (", in-place NCCL all-gather per frame" if world > 1 else ""))
+                           if gather not in ("p2p", "p2p-nccl") else f"16x16-pixel blocks interleaved over {world} ranks, peer stores into rank 0's frame over NVLink + " + ("release/acquire flag hand-over" if gather == "p2p" else "4-byte all-reduce") + " per frame",
+                           "gather": gather,
+                           "l2": "flushed between timed iterations (256 MiB memset outside the timed event pairs); "
+                                 "the scene is 3.4 KB and lives in shared memory",
+                           "arithmetic": ("RT_FLAG_STRICT_IEEE: reference operation sequence, frames bit-identical to the reference's" if args.strict else
+                                          "fast path (FMA, division-free shadow tests), within 1/255 on >= 99.9 % of pixels; "
+                                          "bit_exact_mode = the same frame through RT_FLAG_STRICT_IEEE")},
+                "also_4k": also_4k,
+                "wall_ms_per_step_incl_flush": round(t_wall / args.steps * 1e3, 4),
+                "kernel_ms_per_step": round(kern_ms_per_step, 4),
+                "e2e": e2e_line,
+                "gpu_launches": int(launches),
+                "clocks": clocks,
+                "roofline": {"bound": "fp32", "kernel": "draw_fast_kernel<%d,true>" % (10 if cfg.shadow_samples % 10 == 0 else 8),
+                             "achieved": round(achieved, 3), "peak": round(fp32_peak, 3), "unit": "TFLOP/s",
+                             "frac": round(achieved / fp32_peak, 4) if fp32_peak else None,
+                             "peak_source": "FFMA microbenchmark in this run (rt_measure_fp32_peak); MEASURED_PEAKS.json has no FP32 entry",
+                             "peak_nominal": round(nominal, 1), "frac_of_nominal": round(achieved / nominal, 4),
+                             "algorithmic_gflop_per_launch": round(flops / 1e9, 3),
+                             "traffic": load_traffic(cfg.name), "ncu": load_ncu(cfg.name),
+                             "note": "achieved = ALGORITHMIC FLOPs of the reference's brute-force algorithm (SURVEY.md 8d) / kernel time; the "
+                                     "kernel executes fewer: conservative culls (tile binning, plane/edge/box culls) skip tests the "
+                                     "reference must perform, so frac can exceed 1.  What bounds the kernel is instruction issue and "
+                                     "latency (see ncu: issue slots and FMA pipe utilisation), not FMA throughput."},
+            }
+            if mesh:
+                # BVH path: no FLOP bound.  Algorithmic bytes: a binary BVH with 4-triangle leaves needs
+                # ceil(log2(N/4)) = 19 node visits x 64 B + 4 triangles x 48 B = 1.4 KB per ray.
+                bytes_per_ray = 19 * 64 + 4 * 48
+                peaks = {}
                 try:
-                    from oracle import bind as ob
-                    if ob.ref_ocl_available():
-                        scene_o, rot_o, cam_o, light_o = scene_and_camera(cfg.name)
-                        _, info = ob.ref_ocl_render(cfg.width, cfg.height, cfg.aa, cfg.shadow_samples, cfg.max_bounces, cfg.focal,
-                                                    scene_o.verts, scene_o.normals, scene_o.colors, rot_o, cam_o, light_o, frames=5)
-                        full = load_counts(cfg.name)["rays"]
-                        line["cpu_baseline"]["same_gpu_opencl"] = {
-                            "what": "reference kernels.cl `draw`, -cl-fast-relaxed-math -cl-mad-enable, NDRange {W,H}/{128,4}",
-                            "device": info["device"], "kernel_ms": round(info["kernel_ms"], 4),
-                            "offload_rendering_ms": round(info["total_ms"], 4),
-                            "value": round(full / info["kernel_ms"] / 1e3, 2), "unit": UNIT}
-                except Exception as e:  # noqa: BLE001 - optional yardstick
-                    line["cpu_baseline"]["same_gpu_opencl"] = {"unavailable": str(e)[:200]}
-        print(json.dumps(line), flush=True)
-    torch.cuda.synchronize()
-    r.synchronize()  # surfaces a timed-out rt_peer_wait
-    if dist is not None:
-        dist.barrier()
-    if peer_ptr:
-        r.ipc_close_frame(peer_ptr)
-    if dist is not None:
-        dist.barrier()
-    r.close()
+                    with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+                        peaks = json.load(f)
+                except Exception:
+                    pass
+                peak = float(peaks.get("hbm_gbs", 6650.0))
+                ach = bytes_per_ray * counts["rays"] / world / (kern_ms_per_step * 1e-3) / 1e9
+                line["roofline"] = {"bound": "hbm", "kernel": "draw_bvh_kernel<float,8>", "achieved": round(ach, 1), "peak": peak,
+                                    "unit": "GB/s", "frac": round(ach / peak, 4),
+                                    "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 GB/s (of fallback)",
+                                    "algorithmic_bytes_per_ray": bytes_per_ray, "traffic": load_traffic(cfg.name), "ncu": load_ncu(cfg.name),
+                                    "note": "nodes 42 MB + triangles 63 MB stay in the 126 MB L2 (ncu: DRAM 0.1 %, L2 0.9 %, L1 22 % of peak): the "
+                                            "traversal is latency / issue-bound inside the SM, the byte figure is only the SURVEY 8d yardstick"}
+            if world == 1 and not args.strict:
+                # the bit-exact path (frames identical to the reference's), same frame, device time
+                with u.Renderer(W, H, cfg.aa, cfg.shadow_samples, cfg.max_bounces, device=local_rank, strict=True) as rs:
+                    rs.upload_scene(scene)
+                    ms = []
+                    for _ in range(8):
+                        rs.render_device(rot, cam4, light4, cfg.focal)
+                        ms.append(rs.last_kernel_ms)
+                    best = min(ms[3:])
+                line["bit_exact_mode"] = {"flag": "RT_FLAG_STRICT_IEEE", "kernel_ms_per_step": round(best, 4),
+                                          "value": round(counts["rays"] / best / 1e3, 2), "unit": UNIT,
+                                          "note": "same culls, surviving tests and all shading in the reference's IEEE operation sequence"}
+            # CPU baseline on this box's host cores (N = 1 only)
+            if world == 1 and not args.no_cpu_baseline:
+                step = pick_row_step(cfg)
+                best, rays, kind = None, 0, "reference"
+                t_budget = time.perf_counter()
+                for i in range(1 if mesh else 6):
+                    t, rays, kind = cpu_reference_frame(cfg, step)
+                    best = t if best is None else min(best, t)
+                    if time.perf_counter() - t_budget > 15.0:
+                        break
+                line["cpu_baseline"] = {
+                    "value": round(rays / best / 1e6, 2), "unit": UNIT, "cores": os.cpu_count(), "kind": kind,
+                    "sample": ("cfg4 scene at 480x270, one row through the mesh" if mesh else f"{cfg.name}, " + ("all rows" if step == 1 else f"every {step}th row")) +
+                              f", best of {i + 1} frames; verbatim kernels.cl via g++ shim (-O2, strict IEEE), all host threads",
+                    "ms_per_frame": None if mesh else round(best * step * 1e3, 1)}
+                if not mesh:
+                    try:  # the optimiser-let-loose build of the same text, reported separately (not bit-reproducible)
+                        from oracle import bind as ob
+                        if ob.ref_speed_available(cfg.aa, cfg.shadow_samples, cfg.max_bounces):
+                            tb = min(cpu_reference_frame(cfg, step, speed=True)[0] for _ in range(3))
+                            line["cpu_baseline"]["speed_build"] = {"value": round(rays / tb / 1e6, 2), "unit": UNIT,
+                                                                   "flags": "-O3 -march=x86-64-v3 -ffp-contract=fast",
+                                                                   "ms_per_frame": round(tb * step * 1e3, 1)}
+                    except Exception as e:  # noqa: BLE001
+                        line["cpu_baseline"]["speed_build"] = {"unavailable": str(e)[:200]}
+                    # Same-box GPU yardstick, still the baseline leg: the reference's own OpenCL kernel on THIS B200 through
+                    # NVIDIA's OpenCL driver (oracle/ref_ocl.c; parameter tokens substituted for cfg != HEAD).  Reported, never used.
+                    try:
+                        from oracle import bind as ob
+                        if ob.ref_ocl_available():
+                            scene_o, rot_o, cam_o, light_o = scene_and_camera(cfg.name)
+                            _, info = ob.ref_ocl_render(cfg.width, cfg.height, cfg.aa, cfg.shadow_samples, cfg.max_bounces, cfg.focal,
+                                                        scene_o.verts, scene_o.normals, scene_o.colors, rot_o, cam_o, light_o, frames=5)
+                            full = load_counts(cfg.name)["rays"]
+                            line["cpu_baseline"]["same_gpu_opencl"] = {
+                                "what": "reference kernels.cl `draw`, -cl-fast-relaxed-math -cl-mad-enable, NDRange {W,H}/{128,4}",
+                                "device": info["device"], "kernel_ms": round(info["kernel_ms"], 4),
+                                "offload_rendering_ms": round(info["total_ms"], 4),
+                                "value": round(full / info["kernel_ms"] / 1e3, 2), "unit": UNIT}
+                    except Exception as e:  # noqa: BLE001 - optional yardstick
+                        line["cpu_baseline"]["same_gpu_opencl"] = {"unavailable": str(e)[:200]}
+            print(json.dumps(line), flush=True)
+        torch.cuda.synchronize()
+        r.synchronize()  # surfaces a timed-out rt_peer_wait
+        if dist is not None:
+            dist.barrier()
+        if peer_ptr:
+            r.ipc_close_frame(peer_ptr)
+        if dist is not None:
+            dist.barrier()
+        r.close()
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()
@@ -576,6 +609,7 @@ def main() -> int:
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
     ap.add_argument("--workload", default="cfg2")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-4k", action="store_true", help="skip the short cfg3 (4K) measurement reported as also_4k")
     ap.add_argument("--strict", action="store_true", help="time the bit-exact path (RT_FLAG_STRICT_IEEE) instead of the fast one")
     ap.add_argument("--gather", choices=["auto", "nccl", "p2p", "p2p-nccl"], default="auto",
                     help="N>1: how the frame reaches rank 0 (auto = p2p)")
