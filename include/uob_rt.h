@@ -49,7 +49,15 @@ enum {
   /* With RT_FLAG_STRICT_IEEE: the reference's plain loop structure (every ray against every triangle), without the
    * conservative culls the strict path otherwise shares with the fast one.  Same frame bit for bit, several times
    * slower; kept as the anchor the culled strict path is tested against. */
-  RT_FLAG_REFERENCE_LOOPS = 1u << 4
+  RT_FLAG_REFERENCE_LOOPS = 1u << 4,
+  /* Four lanes per pixel (each traces every fourth ray of the pixel's aa*aa; aa = 2 or 4 only).  Same frame.  The
+   * default picks it by itself for launches too small to fill the GPU (a share of a frame on 4 or 8 GPUs), where
+   * the launch lasts as long as its slowest pixel; these two flags force it on or off. */
+  RT_FLAG_SPLIT_PIXELS = 1u << 5,
+  RT_FLAG_NO_SPLIT = 1u << 6,
+  /* Four lanes per pixel only for the tiles that can see a sphere (the pixels with mirror / glass bounce chains), ordinary
+   * mapping elsewhere, in one launch.  What the default chooses for small launches. */
+  RT_FLAG_SPLIT_HEAVY = 1u << 7
 };
 
 /* Everything that is a compile-time constant in the reference

@@ -25,6 +25,9 @@ RT_FLAG_FORCE_BRUTE = 1 << 1
 RT_FLAG_FORCE_BVH = 1 << 2
 RT_FLAG_COUNT_RAYS = 1 << 3
 RT_FLAG_REFERENCE_LOOPS = 1 << 4
+RT_FLAG_SPLIT_PIXELS = 1 << 5
+RT_FLAG_NO_SPLIT = 1 << 6
+RT_FLAG_SPLIT_HEAVY = 1 << 7
 
 
 class RtConfig(ctypes.Structure):

@@ -7,6 +7,7 @@
 #include <utility>
 
 #include "rt_internal.h"
+#include "rt_launch.cuh"
 #include "rt_types.h"
 
 static thread_local std::string g_create_err;
@@ -28,16 +29,138 @@ namespace rt {
 // around the image centre and the cheapest (background outside the box) at its edges; in row-major
 // order the last rows start when the frame is almost done and their long blocks run alone.
 // Starting tiles centre-out removes that tail (60 us of a 355 us 1080p frame).
-const int *tile_order_for(rt_ctx *ctx, int row0, int rows, int grid_x, int n_blocks) {
-  const int grid_y = n_blocks / (grid_x > 0 ? grid_x : 1);
-  const int tile_h = rows > 0 && grid_y > 0 ? (rows + grid_y - 1) / grid_y : 16;
+// Four lanes per pixel pay off when the launch cannot fill the GPU for long: its duration is then set by its slowest
+// blocks, the tiles whose pixels run mirror / glass bounce chains.  kSplitHeavy (mixed launch) splits only those tiles.
+// RT_FLAG_SPLIT_PIXELS / RT_FLAG_SPLIT_HEAVY / RT_FLAG_NO_SPLIT force a mode; default: by the size of the launch.
+// Measured on B200 (scripts/gpu_split.py; 1/N block-interleaved shares of cfg2, HEAD and cfg3): the mixed launch wins
+// below ~10 k pixels per SM (1080p on 2+ GPUs: 129 -> 112 us at 1/2, 87 -> 56 us at 1/8; the 1024^2 HEAD frame on one
+// GPU: 221 -> 214 us; 4K on 8 GPUs: 427 -> 329 us) and loses a few per cent above (4K on 2 GPUs).
+constexpr double kSplitBelowPixelsPerSm = 10000.0;
+SplitMode split_mode(const rt_ctx *ctx, const FrameParams &fp) {
+  const int R = fp.A * fp.A;
+  if (R != 4 && R != 16) return kSplitNone;
+  if (ctx->cfg.flags & RT_FLAG_NO_SPLIT) return kSplitNone;
+  if (ctx->cfg.flags & RT_FLAG_SPLIT_PIXELS) return kSplitAll;
+  if (ctx->cfg.flags & RT_FLAG_SPLIT_HEAVY) return kSplitHeavy;
+  const int stride = ctx->cfg.block_stride > 1 ? ctx->cfg.block_stride : 1;
+  const double pixels_per_sm = (double)fp.W * fp.rows / stride / (ctx->sm_count > 0 ? ctx->sm_count : 148);
+  return pixels_per_sm < kSplitBelowPixelsPerSm ? kSplitHeavy : kSplitNone;
+}
+
+// Can a primary ray of the 16x16 tile at (tile_x, tile_y) reach one of the two spheres?  Host-side version of the cone
+// test in the kernel prologue, a little wider; it only chooses the lane mapping of the tile.
+static bool tile_may_see_sphere(const FrameParams &fp, int tile_x, int tile_y) {
+  const float A = (float)fp.A;
+  const float vx0 = (float)(tile_x * fp.A) - (float)fp.W * A * 0.5f, vy0 = (float)(tile_y * fp.A) - (float)fp.H * A * 0.5f;
+  const float vx1 = vx0 + (float)(kTileW * fp.A - 1), vy1 = vy0 + (float)(kTileH * fp.A - 1);
+  float dc[4][3], dm[3] = {0, 0, 0};
+  for (int c = 0; c < 4; c++) {
+    const float vx = (c & 1) ? vx1 : vx0, vy = (c & 2) ? vy1 : vy0;
+    for (int r = 0; r < 3; r++) dc[c][r] = fp.rot[3 * r] * vx + fp.rot[3 * r + 1] * vy + fp.rot[3 * r + 2] * fp.focal;
+  }
+  for (int r = 0; r < 3; r++) dm[r] = 0.5f * (dc[0][r] + dc[3][r]);
+  const float lm = sqrtf(dm[0] * dm[0] + dm[1] * dm[1] + dm[2] * dm[2]);
+  float cos_t = 1.0f;
+  for (int c = 0; c < 4; c++) {
+    const float lc = sqrtf(dc[c][0] * dc[c][0] + dc[c][1] * dc[c][1] + dc[c][2] * dc[c][2]);
+    cos_t = fminf(cos_t, (dm[0] * dc[c][0] + dm[1] * dc[c][1] + dm[2] * dc[c][2]) / (lm * lc));
+  }
+  if (!(cos_t > 0.0f)) return true;
+  const float th_t = acosf(fminf(cos_t, 1.0f));
+  for (int i = 0; i < RT_SPHERES; i++) {
+    const float L[3] = {rt::kSphereCenterR2[i][0] - fp.cam[0], rt::kSphereCenterR2[i][1] - fp.cam[1], rt::kSphereCenterR2[i][2] - fp.cam[2]};
+    const float l2 = L[0] * L[0] + L[1] * L[1] + L[2] * L[2], r2 = rt::kSphereCenterR2[i][3];
+    if (l2 <= r2 * 1.001f) return true;
+    const float th_s = asinf(fminf(sqrtf(r2 / l2), 1.0f));
+    const float cosang = (dm[0] * L[0] + dm[1] * L[1] + dm[2] * L[2]) / (lm * sqrtf(l2));
+    if (acosf(fmaxf(fminf(cosang, 1.0f), -1.0f)) <= th_t + th_s + 2e-3f) return true;
+  }
+  return false;
+}
+
+bool mixed_tables_for(rt_ctx *ctx, const FrameParams &fp, cudaStream_t stream, const int **light, int *n_light, const int **split,
+                      int *n_split) {
+  float key[16] = {fp.rot[0], fp.rot[1], fp.rot[2], fp.rot[3], fp.rot[4], fp.rot[5], fp.rot[6], fp.rot[7], fp.rot[8],
+                   fp.cam[0], fp.cam[1], fp.cam[2], fp.focal, (float)fp.A, (float)fp.row0, (float)fp.rows};
+  rt_ctx::MixedTables *hit = nullptr, *victim = &ctx->mixed[0];
+  for (auto &e : ctx->mixed) {
+    if (e.valid && memcmp(key, e.key, sizeof key) == 0) hit = &e;
+    if (!e.valid ? victim->valid : (victim->valid && e.last_use < victim->last_use)) victim = &e;
+  }
+  rt_ctx::MixedTables &m = hit ? *hit : *victim;
+  m.last_use = ++ctx->mixed_clock;
+  if (!hit) {
+    const int gx = (fp.W + kTileW - 1) / kTileW, gy = (fp.rows + kTileH - 1) / kTileH;
+    const int sgx = (fp.W + kSplitTileW - 1) / kSplitTileW;
+    const float cx = 0.5f * (float)fp.W, cy = 0.5f * (float)fp.H;
+    std::vector<std::pair<float, int>> lt, st;
+    for (int by = 0; by < gy; by++)
+      for (int bx = 0; bx < gx; bx++) {
+        const int tx = bx * kTileW, ty = fp.row0 + by * kTileH;
+        if (!tile_may_see_sphere(fp, tx, ty)) {
+          const float x = (float)(tx + kTileW / 2) - cx, y = (float)(ty + kTileH / 2) - cy;
+          lt.emplace_back(x * x + y * y, by * gx + bx);
+          continue;
+        }
+        for (int sy = 0; sy < kTileH / kSplitTileH; sy++)
+          for (int sx = 0; sx < kTileW / kSplitTileW; sx++) {
+            const int px = tx + sx * kSplitTileW, py = ty + sy * kSplitTileH;
+            if (px >= fp.W || py >= fp.row0 + fp.rows) continue;
+            const float x = (float)(px + kSplitTileW / 2) - cx, y = (float)(py + kSplitTileH / 2) - cy;
+            st.emplace_back(x * x + y * y, (by * (kTileH / kSplitTileH) + sy) * sgx + bx * (kTileW / kSplitTileW) + sx);
+          }
+      }
+    std::sort(lt.begin(), lt.end());
+    std::sort(st.begin(), st.end());
+    std::vector<int> both;
+    both.reserve(lt.size() + st.size() + 1);
+    for (const auto &e : lt) both.push_back(e.second);
+    for (const auto &e : st) both.push_back(e.second);
+    both.push_back(0);
+    // a frame in flight (on any stream of this context) may still be reading the tables this slot held
+    if (m.valid && cudaDeviceSynchronize() != cudaSuccess) {
+      cudaGetLastError();
+      m.valid = false;
+      return false;
+    }
+    if (m.capacity < both.size()) {
+      if (m.d_tables) cudaFree(m.d_tables);
+      m.d_tables = nullptr;
+      m.capacity = 0;
+      if (cudaMalloc(&m.d_tables, sizeof(int) * both.size()) != cudaSuccess) {
+        cudaGetLastError();
+        m.valid = false;
+        return false;
+      }
+      m.capacity = both.size();
+    }
+    // pageable source: the copy is staged before the call returns, and it is ordered before the launch on the stream
+    if (cudaMemcpyAsync(m.d_tables, both.data(), sizeof(int) * both.size(), cudaMemcpyHostToDevice, stream) != cudaSuccess ||
+        cudaStreamSynchronize(stream) != cudaSuccess) {
+      cudaGetLastError();
+      m.valid = false;
+      return false;
+    }
+    m.n_light = (int)lt.size();
+    m.n_split = (int)st.size();
+    memcpy(m.key, key, sizeof key);
+    m.valid = true;
+  }
+  *light = m.d_tables;
+  *n_light = m.n_light;
+  *split = m.d_tables + m.n_light;
+  *n_split = m.n_split;
+  return true;
+}
+
+const int *tile_order_for(rt_ctx *ctx, int row0, int rows, int grid_x, int n_blocks, int tile_w, int tile_h) {
   for (const auto &t : ctx->tile_orders)
-    if (t.row0 == row0 && t.rows == rows && t.tile_h == tile_h) return t.d_order;
+    if (t.row0 == row0 && t.rows == rows && t.tile_h == tile_h && t.tile_w == tile_w) return t.d_order;
   std::vector<std::pair<float, int>> key((size_t)n_blocks);
   const float cx = 0.5f * (float)ctx->cfg.width, cy = 0.5f * (float)ctx->cfg.height;
   for (int b = 0; b < n_blocks; b++) {
     const int by = b / grid_x, bx = b - by * grid_x;
-    const float x = (float)(bx * 16 + 8) - cx, y = (float)(row0 + by * tile_h + tile_h / 2) - cy;
+    const float x = (float)(bx * tile_w + tile_w / 2) - cx, y = (float)(row0 + by * tile_h + tile_h / 2) - cy;
     key[(size_t)b] = std::make_pair(x * x + y * y, b);
   }
   std::sort(key.begin(), key.end());
@@ -53,7 +176,7 @@ const int *tile_order_for(rt_ctx *ctx, int row0, int rows, int grid_x, int n_blo
     cudaFree(d);
     return nullptr;
   }
-  ctx->tile_orders.push_back(rt_ctx::TileOrder{row0, rows, tile_h, d});
+  ctx->tile_orders.push_back(rt_ctx::TileOrder{row0, rows, tile_w, tile_h, d});
   return d;
 }
 
@@ -104,6 +227,8 @@ static int free_ctx(rt_ctx *ctx) {
     if (ctx->slot_copy_done[sl]) cudaEventDestroy(ctx->slot_copy_done[sl]);
   }
   if (ctx->d_frame_alt) cudaFree(ctx->d_frame_alt);
+  for (auto &e : ctx->mixed)
+    if (e.d_tables) cudaFree(e.d_tables);
   if (ctx->ev0) cudaEventDestroy(ctx->ev0);
   if (ctx->ev1) cudaEventDestroy(ctx->ev1);
   if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);

@@ -29,6 +29,8 @@ namespace rt {
 // radius^2 in .w; colour.w is the material (-1 glass, 0 mirror).
 #define RT_SPHERES 2
 static __constant__ float4 c_sphere_center_r2[RT_SPHERES] = {{0.3f, 0.1f, -0.5f, 0.075f}, {-0.4f, 0.8f, -0.5f, 0.05f}};
+// host-side copy (tile classification of mixed launches, rt_api.cu)
+static const float kSphereCenterR2[RT_SPHERES][4] = {{0.3f, 0.1f, -0.5f, 0.075f}, {-0.4f, 0.8f, -0.5f, 0.05f}};
 static __constant__ float4 c_sphere_color[RT_SPHERES] = {{0.0f, 0.0f, 0.0f, -1.0f}, {0.0f, 0.0f, 0.0f, 0.0f}};
 
 #define RT_GLASS 1.52f

@@ -254,7 +254,7 @@ static cudaError_t launch_bvh_t(rt_ctx *ctx, const FrameParams &fp_in, cudaStrea
   fp.n_blocks = fp.grid_x * ((fp.rows + kTileH - 1) / kTileH);
   fp.blk_stride = ctx->cfg.block_stride > 1 ? ctx->cfg.block_stride : 1;
   fp.blk_phase = ctx->cfg.block_stride > 1 ? ctx->cfg.block_phase : 0;
-  fp.tile_order = tile_order_for(ctx, fp.row0, fp.rows, fp.grid_x, fp.n_blocks);
+  fp.tile_order = tile_order_for(ctx, fp.row0, fp.rows, fp.grid_x, fp.n_blocks, kTileW, kTileH);
   const int my_blocks = (fp.n_blocks - fp.blk_phase + fp.blk_stride - 1) / fp.blk_stride;
   if (my_blocks <= 0) return cudaSuccess;
   draw_bvh_kernel<T, CH><<<my_blocks, kThreads, 0, stream>>>(fp, *static_cast<const BvhView *>(ctx->bvh_view));

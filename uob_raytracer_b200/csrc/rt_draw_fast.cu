@@ -11,9 +11,14 @@ namespace rt {
 // CH shadow samples per chunk, SINGLE = (S == CH).  STRICT = RT_FLAG_STRICT_IEEE: same binning, culls and
 // caster lists, but every test that survives them — and all shading arithmetic — runs the reference's exact
 // operation sequence, so the frame is bit-identical to the reference's (and to draw_brute_kernel<sfloat>).
-template <int CH, bool SINGLE, bool STRICT>
-__global__ void __launch_bounds__(kThreads, STRICT ? 2 : RT_MINBLOCKS) draw_fast_kernel(const __grid_constant__ FrameParams p,
-                                                                           const float4 *__restrict__ scene, int n, int n_sh) {
+//
+// SPLIT: four lanes per pixel, each tracing every fourth ray of the pixel's A*A (A = 2 or 4), 8x8-pixel tiles.  Same
+// frame; used when a launch is too small to fill the GPU (a 1/4 or 1/8 share of a 1080p frame): the launch then ends
+// with its slowest pixel, a glass-sphere pixel whose A*A rays x several bounces form one serial chain — split four
+// ways.  Per-ray contributions are parked and summed in the reference's ray order, so STRICT stays bit-identical.
+template <int CH, bool SINGLE, bool STRICT, bool SPLIT>
+__device__ __forceinline__ void draw_fast_body(const FrameParams &p, const float4 *__restrict__ scene, int n, int n_sh, int block,
+                                               const int *order, int grid_x) {
   extern __shared__ float4 smem[];
   __shared__ int s_warp_count[kThreads / 32];
   __shared__ int s_base;
@@ -50,7 +55,8 @@ __global__ void __launch_bounds__(kThreads, STRICT ? 2 : RT_MINBLOCKS) draw_fast
   const float SW = (float)p.W, SH = (float)p.H, fA = (float)A;
   if (threadIdx.x == 0) s_base = 0;
   int x, y, tile_x, tile_y;
-  const bool in_frame = pixel_of_thread(p, x, y, tile_x, tile_y);
+  const bool in_frame = pixel_of_thread<SPLIT>(p, block, order, grid_x, x, y, tile_x, tile_y);
+  constexpr int kTW = SPLIT ? kSplitTileW : kTileW, kTH = SPLIT ? kSplitTileH : kTileH;
   __syncthreads();
 
   // ---- per-triangle camera constants + binning of the triangles against this block's tile ----
@@ -59,7 +65,7 @@ __global__ void __launch_bounds__(kThreads, STRICT ? 2 : RT_MINBLOCKS) draw_fast
     // corner rays of the tile in virtual (sub-pixel) coordinates, un-normalised (kernels.cl:384-400)
     const float vx0 = (float)(tile_x * A) - SW * fA * 0.5f;
     const float vy0 = (float)(tile_y * A) - SH * fA * 0.5f;
-    const float vx1 = vx0 + (float)(kTileW * A - 1), vy1 = vy0 + (float)(kTileH * A - 1);
+    const float vx1 = vx0 + (float)(kTW * A - 1), vy1 = vy0 + (float)(kTH * A - 1);
     V3<float> dc[4];
     float dmax = 0.0f;
 #pragma unroll
@@ -133,6 +139,10 @@ __global__ void __launch_bounds__(kThreads, STRICT ? 2 : RT_MINBLOCKS) draw_fast
   __syncthreads();
   sc.n_prim = s_base;
   const bool spheres_visible = s_spheres_visible != 0;
+#ifdef RT_DEBUG_PROLOGUE_ONLY  // experiment: cost of staging + binning alone
+  if (in_frame) p.out[(size_t)y * p.W + x] = 0xff000000u | (unsigned)sc.n_prim;
+  return;
+#endif
   if (sc.n_prim == 0 && !spheres_visible) {
     // nothing can be hit from this tile (at 1080p 44 % of the frame lies beside the box): every ray misses, the
     // pixel is the average of A*A black samples (kernels.cl:404-425)
@@ -160,7 +170,8 @@ __global__ void __launch_bounds__(kThreads, STRICT ? 2 : RT_MINBLOCKS) draw_fast
   V3<float> total(0.0f, 0.0f, 0.0f);
   V3<SF> total_s(SF(0.0f), SF(0.0f), SF(0.0f));  // STRICT accumulates in the reference's order and arithmetic
   const V3<SF> light_s(SF(light.x), SF(light.y), SF(light.z));
-  const int rays = A * A;
+  const int split_q = SPLIT ? (int)(threadIdx.x & 3u) : 0;  // SPLIT: this lane traces rays split_q, split_q + 4, ...
+  const int rays = SPLIT ? (A * A) >> 2 : A * A;
   // Rays of a pixel are processed in groups of kGroup, in the reference's order dy*A + dx
   // (kernels.cl:393-397).  Phase 1 finds the primary hit of each ray of the group and parks it in this
   // thread's shared-memory column; phase 2 builds ONE shadow-caster list for the warp from the bounding
@@ -176,11 +187,16 @@ __global__ void __launch_bounds__(kThreads, STRICT ? 2 : RT_MINBLOCKS) draw_fast
     int first_dx = ray_dx, first_dy = ray_dy;
 #pragma unroll 1
     for (int k = 0; k < group; k++) {
-      const V3<SF> d0 = base + V3<SF>(SF((float)ray_dx), SF((float)ray_dy), SF(0.0f));
-      if (++ray_dx == A) {
+      int cur_dx = ray_dx, cur_dy = ray_dy;
+      if constexpr (SPLIT) {
+        const int idx = split_q + 4 * (g0 + k);
+        cur_dy = idx / A;
+        cur_dx = idx - cur_dy * A;
+      } else if (++ray_dx == A) {
         ray_dx = 0;
         ray_dy++;
       }
+      const V3<SF> d0 = base + V3<SF>(SF((float)cur_dx), SF((float)cur_dy), SF(0.0f));
       const V3<SF> dns = normalize(V3<SF>(dot(r0, d0), dot(r1, d0), dot(r2, d0)));
       int bi;
       float bt, bu, bv;
@@ -247,7 +263,7 @@ __global__ void __launch_bounds__(kThreads, STRICT ? 2 : RT_MINBLOCKS) draw_fast
     // Phase 3 — shade the parked hits
 #pragma unroll 1
     for (int k = 0; k < group; k++) {
-      const float *q = rec + k * kRec * kThreads;
+      float *q = rec + k * kRec * kThreads;
       HitRec<float> hit;
       hit.id = __float_as_int(q[0]);
       hit.point = V3<float>(q[1 * kThreads], q[2 * kThreads], q[3 * kThreads]);
@@ -258,7 +274,7 @@ __global__ void __launch_bounds__(kThreads, STRICT ? 2 : RT_MINBLOCKS) draw_fast
       V3<SF> dir_s(SF(0.0f), SF(0.0f), SF(0.0f));
       if (hit.id != -1 && hit.color.w <= 0.0f) {
         // mirror / glass: the bounce needs the ray direction again (same strict sequence as phase 1)
-        const int idx = first_dy * A + first_dx + k;
+        const int idx = SPLIT ? split_q + 4 * (g0 + k) : first_dy * A + first_dx + k;
         const int ddy = idx / A, ddx = idx - ddy * A;
         const V3<SF> d0 = base + V3<SF>(SF((float)ddx), SF((float)ddy), SF(0.0f));
         dir_s = normalize(V3<SF>(dot(r0, d0), dot(r1, d0), dot(r2, d0)));
@@ -269,6 +285,11 @@ __global__ void __launch_bounds__(kThreads, STRICT ? 2 : RT_MINBLOCKS) draw_fast
       // the same shading — a single call site for both
       float medium = RT_AIR;
       int bounce = 0;
+      if constexpr (SPLIT) {  // this ray's contribution, parked in its record slot (black unless shaded below)
+        q[1 * kThreads] = 0.0f;
+        q[2 * kThreads] = 0.0f;
+        q[3 * kThreads] = 0.0f;
+      }
       if constexpr (STRICT) {
         HitRec<SF> hs;
         hs.id = hit.id;
@@ -289,7 +310,14 @@ __global__ void __launch_bounds__(kThreads, STRICT ? 2 : RT_MINBLOCKS) draw_fast
             const SF dl = direct_light_strict<CH, SINGLE, JittersShared<CH, kThreads>>(sc, hs.point, hs.normal, light_s, S, global_id, jit);
             const V3<SF> lightv(SF(RT_INDIRECT) + dl, SF(RT_INDIRECT) + dl, SF(RT_INDIRECT) + dl);
             // primary: colour*(indirect + direct) (kernels.cl:422); after a bounce: 0.9*light*colour (:355)
-            total_s = total_s + (bounced ? scale(SF(0.9f), lightv) * xyz<SF>(hs.color) : xyz<SF>(hs.color) * lightv);
+            const V3<SF> contrib = bounced ? scale(SF(0.9f), lightv) * xyz<SF>(hs.color) : xyz<SF>(hs.color) * lightv;
+            if constexpr (SPLIT) {
+              q[1 * kThreads] = contrib.x.v;
+              q[2 * kThreads] = contrib.y.v;
+              q[3 * kThreads] = contrib.z.v;
+            } else {
+              total_s = total_s + contrib;
+            }
             break;
           }
           if (bounce >= p.B) break;
@@ -319,7 +347,13 @@ __global__ void __launch_bounds__(kThreads, STRICT ? 2 : RT_MINBLOCKS) draw_fast
             have_jit = true;
           }
           const float fl = gain * (RT_INDIRECT + direct_light_fast<CH, SINGLE, JittersShared<CH, kThreads>>(sc, hit.point, hit.normal, light, S, global_id, jit));
-          total = V3<float>(total.x + hit.color.x * fl, total.y + hit.color.y * fl, total.z + hit.color.z * fl);
+          if constexpr (SPLIT) {
+            q[1 * kThreads] = hit.color.x * fl;
+            q[2 * kThreads] = hit.color.y * fl;
+            q[3 * kThreads] = hit.color.z * fl;
+          } else {
+            total = V3<float>(total.x + hit.color.x * fl, total.y + hit.color.y * fl, total.z + hit.color.z * fl);
+          }
           break;
         }
         if (bounce >= p.B) break;
@@ -338,6 +372,18 @@ __global__ void __launch_bounds__(kThreads, STRICT ? 2 : RT_MINBLOCKS) draw_fast
       }
     }
   }
+  if constexpr (SPLIT) {
+    // the pixel's first lane sums the parked contributions in the reference's ray order (kernels.cl:415-425)
+    __syncwarp(warp_mask);
+    if (split_q != 0) return;
+    for (int j = 0; j < rays; j++)
+      for (int qq = 0; qq < 4; qq++) {
+        const float *c = rec + qq + j * kRec * kThreads;
+        const V3<float> v(c[1 * kThreads], c[2 * kThreads], c[3 * kThreads]);
+        if constexpr (STRICT) total_s = total_s + V3<SF>(SF(v.x), SF(v.y), SF(v.z));
+        else total = V3<float>(total.x + v.x, total.y + v.y, total.z + v.z);
+      }
+  }
   if constexpr (STRICT) {
     const SF fa = SF(__int2float_rn(A * A));
     p.out[(size_t)y * p.W + x] = pack_argb<SF>(V3<SF>(div_(total_s.x, fa), div_(total_s.y, fa), div_(total_s.z, fa)));
@@ -347,18 +393,53 @@ __global__ void __launch_bounds__(kThreads, STRICT ? 2 : RT_MINBLOCKS) draw_fast
   p.out[(size_t)y * p.W + x] = pack_argb<float>(V3<float>(total.x * ia, total.y * ia, total.z * ia));
 }
 
+template <int CH, bool SINGLE, bool STRICT, bool SPLIT>
+__global__ void __launch_bounds__(kThreads, STRICT ? 2 : RT_MINBLOCKS) draw_fast_kernel(const __grid_constant__ FrameParams p,
+                                                                           const float4 *__restrict__ scene, int n, int n_sh) {
+  draw_fast_body<CH, SINGLE, STRICT, SPLIT>(p, scene, n, n_sh, (int)blockIdx.x, p.tile_order, p.grid_x);
+}
+
+// Mixed launch for shares of a frame that cannot fill the GPU: tiles that can see a sphere (mirror / glass bounce chains,
+// the pixels a small launch ends up waiting for) are rendered as four 8x8 sub-tiles with four lanes per pixel, by the
+// first n_split blocks of the grid; every other tile by an ordinary block.  The host classifies the tiles per camera
+// (rt_api.cu: mixed_tables_for); the classification only steers performance — either mapping renders any tile correctly.
+template <int CH, bool SINGLE, bool STRICT>
+__global__ void __launch_bounds__(kThreads, STRICT ? 2 : RT_MINBLOCKS) draw_fast_mixed_kernel(const __grid_constant__ FrameParams p,
+                                                                                 const float4 *__restrict__ scene, int n, int n_sh) {
+  if ((int)blockIdx.x < p.n_split)
+    draw_fast_body<CH, SINGLE, STRICT, true>(p, scene, n, n_sh, (int)blockIdx.x, p.split_order, p.split_grid_x);
+  else
+    draw_fast_body<CH, SINGLE, STRICT, false>(p, scene, n, n_sh, (int)blockIdx.x - p.n_split, p.tile_order, p.grid_x);
+}
+
 #define RT_CAT2(a, b) a##b
 #define RT_CAT(a, b) RT_CAT2(a, b)
 
 cudaError_t RT_CAT(launch_fast_ch, RT_FAST_CH)(rt_ctx *ctx, const FrameParams &fp, cudaStream_t stream) {
   constexpr int CH = RT_FAST_CH;
   ctx->launch_extra_smem = sizeof(float) * (3 * CH + 4 * 7) * kThreads;  // jitter columns + parked primary hits
-  if (ctx->cfg.flags & RT_FLAG_STRICT_IEEE) {
-    if (fp.S == CH) return launch_kernel(draw_fast_kernel<CH, true, true>, ctx, fp, stream);
-    return launch_kernel(draw_fast_kernel<CH, false, true>, ctx, fp, stream);
+  const bool strict = (ctx->cfg.flags & RT_FLAG_STRICT_IEEE) != 0, single = fp.S == CH;
+  const SplitMode mode = split_mode(ctx, fp);
+  if (mode == kSplitHeavy) {
+    const int *light = nullptr, *split = nullptr;
+    int n_light = 0, n_split = 0;
+    if (mixed_tables_for(ctx, fp, stream, &light, &n_light, &split, &n_split)) {
+      if (strict) return single ? launch_kernel_mixed(draw_fast_mixed_kernel<CH, true, true>, ctx, fp, stream, light, n_light, split, n_split)
+                                : launch_kernel_mixed(draw_fast_mixed_kernel<CH, false, true>, ctx, fp, stream, light, n_light, split, n_split);
+      return single ? launch_kernel_mixed(draw_fast_mixed_kernel<CH, true, false>, ctx, fp, stream, light, n_light, split, n_split)
+                    : launch_kernel_mixed(draw_fast_mixed_kernel<CH, false, false>, ctx, fp, stream, light, n_light, split, n_split);
+    }
   }
-  if (fp.S == CH) return launch_kernel(draw_fast_kernel<CH, true, false>, ctx, fp, stream);
-  return launch_kernel(draw_fast_kernel<CH, false, false>, ctx, fp, stream);
+  if (mode == kSplitAll) {
+    if (strict) return single ? launch_kernel(draw_fast_kernel<CH, true, true, true>, ctx, fp, stream, kSplitTileW, kSplitTileH)
+                              : launch_kernel(draw_fast_kernel<CH, false, true, true>, ctx, fp, stream, kSplitTileW, kSplitTileH);
+    return single ? launch_kernel(draw_fast_kernel<CH, true, false, true>, ctx, fp, stream, kSplitTileW, kSplitTileH)
+                  : launch_kernel(draw_fast_kernel<CH, false, false, true>, ctx, fp, stream, kSplitTileW, kSplitTileH);
+  }
+  if (strict) return single ? launch_kernel(draw_fast_kernel<CH, true, true, false>, ctx, fp, stream)
+                            : launch_kernel(draw_fast_kernel<CH, false, true, false>, ctx, fp, stream);
+  return single ? launch_kernel(draw_fast_kernel<CH, true, false, false>, ctx, fp, stream)
+                : launch_kernel(draw_fast_kernel<CH, false, false, false>, ctx, fp, stream);
 }
 
 }  // namespace rt

@@ -50,8 +50,21 @@ struct rt_ctx {
   bool peer_waits = false;
   size_t launch_extra_smem = 0;
   // launch-order tables keyed by (row0, rows): centre-out order of the 16-row block grid
-  struct TileOrder { int row0, rows, tile_h; int *d_order; };
+  struct TileOrder { int row0, rows, tile_w, tile_h; int *d_order; };
   std::vector<TileOrder> tile_orders;  // set by a launcher that needs shared memory beyond the scene
+  // launch-order tables of mixed launches (ordinary tiles | split sub-tiles), one entry per (camera, row range):
+  // the row bands of rt_render run concurrently on their own streams, each with its own tables
+  struct MixedTables {
+    bool valid = false;
+    float key[16];
+    int *d_tables = nullptr;
+    size_t capacity = 0;
+    int n_light = 0, n_split = 0;
+    unsigned long long last_use = 0;
+  };
+  static constexpr int kMixedSlots = 8;
+  MixedTables mixed[kMixedSlots];
+  unsigned long long mixed_clock = 0;
   std::string err;
 };
 

@@ -16,6 +16,10 @@ struct FrameParams {
   // optional launch order: tile_order[k] = row-major block number of the k-th block to start
   // (expensive centre tiles first, so that no long-running block is left for the tail)
   const int *tile_order;
+  // mixed launches (rt_draw_fast.cu): the first n_split blocks of the grid render 8x8-pixel sub-tiles with four lanes
+  // per pixel, taken from split_order (numbered row-major on a grid split_grid_x wide); the rest are ordinary blocks
+  int n_split, split_grid_x;
+  const int *split_order;
   int A, S, B;     // AA edge, shadow samples, max bounces
   float focal;
   float rot[9];    // rows r0, r1, r2 (skeleton.cpp:149-151)

@@ -13,7 +13,7 @@ import ctypes
 
 import numpy as np
 
-from ._lib import (RT_FLAG_COUNT_RAYS, RT_FLAG_REFERENCE_LOOPS, RT_FLAG_FORCE_BRUTE, RT_FLAG_FORCE_BVH, RT_FLAG_STRICT_IEEE, RT_OK, RtConfig, c_float_p,
+from ._lib import (RT_FLAG_COUNT_RAYS, RT_FLAG_REFERENCE_LOOPS, RT_FLAG_SPLIT_PIXELS, RT_FLAG_NO_SPLIT, RT_FLAG_SPLIT_HEAVY, RT_FLAG_FORCE_BRUTE, RT_FLAG_FORCE_BVH, RT_FLAG_STRICT_IEEE, RT_OK, RtConfig, c_float_p,
                    rt_lib)
 from .host import Camera, Scene
 
@@ -33,11 +33,13 @@ class Renderer:
     def __init__(self, width: int = 1024, height: int = 1024, aa: int = 2, shadow_samples: int = 10,
                  max_bounces: int = 10, device: int = 0, row0: int = 0, rows: int = 0, strict: bool = False,
                  force_bvh: bool = False, force_brute: bool = False, block_stride: int = 0, block_phase: int = 0, count_rays: bool = False,
-                 reference_loops: bool = False):
+                 reference_loops: bool = False, split_pixels: bool | str | None = None):
         self._lib = rt_lib()
         flags = (RT_FLAG_STRICT_IEEE if strict else 0) | (RT_FLAG_FORCE_BVH if force_bvh else 0) | \
                 (RT_FLAG_FORCE_BRUTE if force_brute else 0) | (RT_FLAG_COUNT_RAYS if count_rays else 0) | \
-                (RT_FLAG_REFERENCE_LOOPS if reference_loops else 0)
+                (RT_FLAG_REFERENCE_LOOPS if reference_loops else 0) | \
+                (0 if split_pixels is None else RT_FLAG_SPLIT_HEAVY if split_pixels == "heavy" else
+                 (RT_FLAG_SPLIT_PIXELS if split_pixels else RT_FLAG_NO_SPLIT))
         self.cfg = RtConfig(width, height, aa, shadow_samples, max_bounces, device, row0, rows, flags, block_stride, block_phase)
         self._ctx = self._lib.rt_create(ctypes.byref(self.cfg))
         if not self._ctx:
