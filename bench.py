@@ -81,8 +81,39 @@ class ClockSampler:
 
     def __init__(self, index: int):
         self.index, self.proc, self.lines = index, None, []
+        self.nvml, self.handle, self.samples, self.stop_flag = None, None, [], False
+
+    def _nvml_handle(self):
+        import pynvml
+        pynvml.nvmlInit()
+        try:  # the CUDA device's own UUID: immune to CUDA_VISIBLE_DEVICES renumbering
+            import torch
+            uuid = str(torch.cuda.get_device_properties(self.index).uuid)
+            h = pynvml.nvmlDeviceGetHandleByUUID(("GPU-" + uuid) if not uuid.startswith("GPU-") else uuid)
+        except Exception:
+            h = pynvml.nvmlDeviceGetHandleByIndex(self.index)
+        return pynvml, h
+
+    def _nvml_loop(self):
+        nv, h = self.nvml, self.handle
+        while not self.stop_flag:
+            try:
+                self.samples.append((nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM), nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM),
+                                     nv.nvmlDeviceGetPowerUsage(h) / 1000.0, nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)))
+            except Exception:
+                pass
+            time.sleep(0.001)
 
     def start(self):
+        # in-process NVML polling at ~1 kHz (a short timed region — 100 frames of 0.1 ms — ends before an nvidia-smi child
+        # has printed its first line); nvidia-smi -lms as the fallback
+        try:
+            self.nvml, self.handle = self._nvml_handle()
+            self.thread = threading.Thread(target=self._nvml_loop, daemon=True)
+            self.thread.start()
+            return
+        except Exception:
+            self.nvml = None
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
                                           "-i", str(self.index), "-lms", "20"], stdout=subprocess.PIPE, text=True)
@@ -96,6 +127,15 @@ class ClockSampler:
             self.lines.append(line.strip())
 
     def stop(self) -> dict:
+        if self.nvml is not None:
+            self.stop_flag = True
+            self.thread.join(timeout=1.0)
+            bits = {"hw_slowdown": 0x8, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20, "sw_power_cap": 0x4}
+            sm = [x[0] for x in self.samples]
+            reasons = sorted({k for x in self.samples for k, b in bits.items() if x[3] & b})
+            return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": float(max(x[1] for x in self.samples)) if sm else None,
+                    "power_w_max": round(max(x[2] for x in self.samples), 1) if sm else None, "samples": len(sm), "reasons": reasons,
+                    "source": "NVML, polled during the timed region"}
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         time.sleep(0.06)
@@ -384,6 +424,7 @@ def run_ours(args, cfg) -> int:
             b.record(stream)
         torch.cuda.synchronize()
         t_wall = time.perf_counter() - t_wall0
+        clocks = sampler.stop() if rank == 0 else {}  # right at the end of the timed region
         launches = r.kernel_launches - launches0
         if dist is not None:
             dist.barrier()
@@ -393,7 +434,12 @@ def run_ours(args, cfg) -> int:
         if dist is not None:
             dist.all_reduce(total_ms, op=dist.ReduceOp.MAX)
         total_step_ms, total_kern_ms = (float(x) for x in total_ms.cpu())
-        clocks = sampler.stop() if rank == 0 else {}
+        per_rank = [round(sum(kern_ms) / steps, 4)]
+        if dist is not None:  # every rank's own kernel time (device events): shows imbalance / hand-over waits
+            mine = torch.tensor([sum(kern_ms) / steps, sum(step_ms) / steps], dtype=torch.float64, device=f"cuda:{local_rank}")
+            allr = [torch.zeros_like(mine) for _ in range(world)]
+            dist.all_gather(allr, mine)
+            per_rank = [[round(float(t[0]), 4), round(float(t[1]), 4)] for t in allr]
 
         if not primary:
             if rank == 0:
@@ -499,6 +545,7 @@ def run_ours(args, cfg) -> int:
                 "also_4k": also_4k,
                 "wall_ms_per_step_incl_flush": round(t_wall / args.steps * 1e3, 4),
                 "kernel_ms_per_step": round(kern_ms_per_step, 4),
+                "per_rank_kernel_and_step_ms": per_rank,
                 "e2e": e2e_line,
                 "gpu_launches": int(launches),
                 "clocks": clocks,
