@@ -47,6 +47,55 @@ SplitMode split_mode(const rt_ctx *ctx, const FrameParams &fp) {
   return pixels_per_sm < kSplitBelowPixelsPerSm ? kSplitHeavy : kSplitNone;
 }
 
+// Pixel rectangle that contains every primary ray able to hit the scene: the eight corners of the scene's bounding box
+// seen from the camera.  A primary ray is cam + t R (vx, vy, f) with R the rotation matrix (rows r0, r1, r2), so a
+// point P lies on the ray through (vx, vy) = f (w.x, w.y) / w.z with w = R^-1 (P - cam).  The hull of the projected
+// corners contains the projection of the box as long as all corners are in front of the camera; otherwise (or if R is
+// singular) the rectangle is the whole frame.  Two pixels of margin absorb the rounding of this float arithmetic.
+void visible_rect(const rt_ctx *ctx, FrameParams &fp) {
+  fp.vis_x0 = 0;
+  fp.vis_y0 = 0;
+  fp.vis_x1 = fp.W;
+  fp.vis_y1 = fp.H;
+  const float *m = fp.rot;
+  const double det = (double)m[0] * (m[4] * m[8] - m[5] * m[7]) - (double)m[1] * (m[3] * m[8] - m[5] * m[6]) +
+                     (double)m[2] * (m[3] * m[7] - m[4] * m[6]);
+  if (!(fabs(det) > 1e-6) || !(fp.focal > 0.0f)) return;
+  double inv[9];
+  inv[0] = (m[4] * m[8] - m[5] * m[7]) / det;
+  inv[1] = (m[2] * m[7] - m[1] * m[8]) / det;
+  inv[2] = (m[1] * m[5] - m[2] * m[4]) / det;
+  inv[3] = (m[5] * m[6] - m[3] * m[8]) / det;
+  inv[4] = (m[0] * m[8] - m[2] * m[6]) / det;
+  inv[5] = (m[2] * m[3] - m[0] * m[5]) / det;
+  inv[6] = (m[3] * m[7] - m[4] * m[6]) / det;
+  inv[7] = (m[1] * m[6] - m[0] * m[7]) / det;
+  inv[8] = (m[0] * m[4] - m[1] * m[3]) / det;
+  double x0 = 1e300, y0 = 1e300, x1 = -1e300, y1 = -1e300;
+  for (int c = 0; c < 8; c++) {
+    const double P[3] = {(c & 1 ? ctx->scene_hi[0] : ctx->scene_lo[0]) - (double)fp.cam[0],
+                         (c & 2 ? ctx->scene_hi[1] : ctx->scene_lo[1]) - (double)fp.cam[1],
+                         (c & 4 ? ctx->scene_hi[2] : ctx->scene_lo[2]) - (double)fp.cam[2]};
+    if (!(fabs(P[0]) < 1e30 && fabs(P[1]) < 1e30 && fabs(P[2]) < 1e30)) return;
+    const double wx = inv[0] * P[0] + inv[1] * P[1] + inv[2] * P[2], wy = inv[3] * P[0] + inv[4] * P[1] + inv[5] * P[2],
+                 wz = inv[6] * P[0] + inv[7] * P[1] + inv[8] * P[2];
+    if (!(wz > 1e-3)) return;  // a corner beside or behind the camera: no bound
+    const double vx = fp.focal * wx / wz, vy = fp.focal * wy / wz;  // virtual (sub-pixel) coordinates, kernels.cl:384-400
+    const double px = (vx + 0.5 * fp.W * fp.A) / fp.A, py = (vy + 0.5 * fp.H * fp.A) / fp.A;
+    x0 = fmin(x0, px);
+    x1 = fmax(x1, px);
+    y0 = fmin(y0, py);
+    y1 = fmax(y1, py);
+  }
+  if (!(x0 <= x1 && y0 <= y1)) return;
+  // pixel x covers sub-pixel rays [x*A, x*A + A - 1] / A: a ray at fractional pixel position q belongs to pixel floor(q)
+  const double lo_x = floor(x0) - 2.0, lo_y = floor(y0) - 2.0, hi_x = floor(x1) + 3.0, hi_y = floor(y1) + 3.0;
+  fp.vis_x0 = (int)fmax(0.0, fmin((double)fp.W, lo_x));
+  fp.vis_y0 = (int)fmax(0.0, fmin((double)fp.H, lo_y));
+  fp.vis_x1 = (int)fmax(0.0, fmin((double)fp.W, hi_x));
+  fp.vis_y1 = (int)fmax(0.0, fmin((double)fp.H, hi_y));
+}
+
 // Can a primary ray of the 16x16 tile at (tile_x, tile_y) reach one of the two spheres?  Host-side version of the cone
 // test in the kernel prologue, a little wider; it only chooses the lane mapping of the tile.
 static bool tile_may_see_sphere(const FrameParams &fp, int tile_x, int tile_y) {
@@ -325,6 +374,29 @@ int rt_upload_scene(rt_ctx *ctx, const float *verts, const float *normals, const
     return RT_ERR_INVALID;
   }
   RT_CUDA(ctx, cudaSetDevice(ctx->cfg.device), "selecting device");
+  // Bounding box of everything a primary ray can hit: the triangles and the two spheres baked into the kernel
+  for (int c = 0; c < 3; c++) {
+    ctx->scene_lo[c] = 3.0e38f;
+    ctx->scene_hi[c] = -3.0e38f;
+  }
+  for (int i = 0; i < RT_SPHERES; i++) {
+    const float r = sqrtf(rt::kSphereCenterR2[i][3]) * 1.0001f;
+    for (int c = 0; c < 3; c++) {
+      ctx->scene_lo[c] = fminf(ctx->scene_lo[c], rt::kSphereCenterR2[i][c] - r);
+      ctx->scene_hi[c] = fmaxf(ctx->scene_hi[c], rt::kSphereCenterR2[i][c] + r);
+    }
+  }
+  for (size_t i = 0; i < 3 * (size_t)n; i++)
+    for (int c = 0; c < 3; c++) {
+      const float v = verts[4 * i + c];
+      if (!(v == v)) {  // NaN vertex: no usable bound
+        ctx->scene_lo[c] = -3.0e38f;
+        ctx->scene_hi[c] = 3.0e38f;
+      } else {
+        ctx->scene_lo[c] = fminf(ctx->scene_lo[c], v);
+        ctx->scene_hi[c] = fmaxf(ctx->scene_hi[c], v);
+      }
+    }
   // Shadow casters: everything except material == -1 (kernels.cl:247)
   int n_sh = 0;
   for (int i = 0; i < n; i++) n_sh += (colors[4 * i + 3] != -1.0f);
@@ -433,6 +505,7 @@ static int render_impl(rt_ctx *ctx, const float rot12[12], const float cam[4], c
     fp.cam[c] = cam[c];
     fp.light[c] = light[c];
   }
+  rt::visible_rect(ctx, fp);
   fp.out = dev_argb ? dev_argb : ctx->d_frame;
   fp.ray_counters = ctx->d_ray_counters;
   if (ctx->d_ray_counters && band_row0 < 0)

@@ -62,6 +62,7 @@ struct rt_ctx {
     int n_light = 0, n_split = 0;
     unsigned long long last_use = 0;
   };
+  float scene_lo[3] = {0, 0, 0}, scene_hi[3] = {0, 0, 0};  // bounding box of the triangles and the two spheres
   static constexpr int kMixedSlots = 8;
   MixedTables mixed[kMixedSlots];
   unsigned long long mixed_clock = 0;

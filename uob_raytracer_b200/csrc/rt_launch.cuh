@@ -66,6 +66,8 @@ __device__ __forceinline__ bool pixel_of_thread(const FrameParams &p, int &x, in
 
 // rt_api.cu: device table of the launch order for a (row0, rows) range, built on first use
 const int *tile_order_for(rt_ctx *ctx, int row0, int rows, int grid_x, int n_blocks, int tile_w, int tile_h);
+// rt_api.cu: fills fp.vis_* (pixel rectangle outside which every primary ray misses the scene)
+void visible_rect(const rt_ctx *ctx, FrameParams &fp);
 // rt_api.cu: how should this launch map lanes to pixels? (flags, AA grid, size of the launch)
 enum SplitMode { kSplitNone = 0, kSplitAll = 1, kSplitHeavy = 2 };
 SplitMode split_mode(const rt_ctx *ctx, const FrameParams &fp);

@@ -20,6 +20,9 @@ struct FrameParams {
   // per pixel, taken from split_order (numbered row-major on a grid split_grid_x wide); the rest are ordinary blocks
   int n_split, split_grid_x;
   const int *split_order;
+  // pixel rectangle [vis_x0, vis_x1) x [vis_y0, vis_y1) outside which no primary ray can hit anything (projection of the
+  // scene's bounding box, rt_api.cu): tiles outside it are black without looking at the scene
+  int vis_x0, vis_y0, vis_x1, vis_y1;
   int A, S, B;     // AA edge, shadow samples, max bounces
   float focal;
   float rot[9];    // rows r0, r1, r2 (skeleton.cpp:149-151)
