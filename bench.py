@@ -273,6 +273,11 @@ def run_reference(args, cfg) -> int:
     return 0
 
 
+# experiment switch (never set in a measured run): peers keep their pixels in their own frame, to separate the cost of
+# the NVLink stores from the rest of the hand-over
+_DEBUG_LOCAL_STORES = bool(os.environ.get("UOB_BENCH_DEBUG_LOCAL_STORES"))
+
+
 def run_ours(args, cfg) -> int:
     import torch
     import uob_raytracer_b200 as u
@@ -367,7 +372,7 @@ def run_ours(args, cfg) -> int:
             fno[0] += 1
             if gather == "p2p" and rank != 0:
                 r.peer_wait(consumed_flag, 1, fno[0] - 1, sptr)  # rank 0 is done with the previous frame
-            r.render_device(rot, cam4, light4, cfg.focal, dev_ptr=target, stream=sptr)
+            r.render_device(rot, cam4, light4, cfg.focal, dev_ptr=(0 if _DEBUG_LOCAL_STORES else target), stream=sptr)
 
         def gather_only(consume=True):
             if gather == "nccl":
@@ -398,7 +403,7 @@ def run_ours(args, cfg) -> int:
                 host.copy_(frame)
             torch.cuda.synchronize()
             alpha = (host.numpy().view(np.uint32) >> 24)
-            if not (alpha == 255).all():
+            if not (alpha == 255).all() and not _DEBUG_LOCAL_STORES:
                 raise SystemExit(f"bench.py: gathered frame incomplete ({int((alpha != 255).sum())} pixels unwritten)")
 
         # ---- device-timed throughput ------------------------------------------------
@@ -436,10 +441,12 @@ def run_ours(args, cfg) -> int:
         total_step_ms, total_kern_ms = (float(x) for x in total_ms.cpu())
         per_rank = [round(sum(kern_ms) / steps, 4)]
         if dist is not None:  # every rank's own kernel time (device events): shows imbalance / hand-over waits
-            mine = torch.tensor([sum(kern_ms) / steps, sum(step_ms) / steps], dtype=torch.float64, device=f"cuda:{local_rank}")
+            mine = torch.tensor([sum(kern_ms) / steps, sum(step_ms) / steps, r.last_kernel_ms], dtype=torch.float64,
+                                device=f"cuda:{local_rank}")
             allr = [torch.zeros_like(mine) for _ in range(world)]
             dist.all_gather(allr, mine)
-            per_rank = [[round(float(t[0]), 4), round(float(t[1]), 4)] for t in allr]
+            # [wait-for-consumed + draw kernel, whole step, draw kernel alone (last frame, the context's own events)]
+            per_rank = [[round(float(t[0]), 4), round(float(t[1]), 4), round(float(t[2]), 4)] for t in allr]
 
         if not primary:
             if rank == 0:
@@ -545,7 +552,7 @@ def run_ours(args, cfg) -> int:
                 "also_4k": also_4k,
                 "wall_ms_per_step_incl_flush": round(t_wall / args.steps * 1e3, 4),
                 "kernel_ms_per_step": round(kern_ms_per_step, 4),
-                "per_rank_kernel_and_step_ms": per_rank,
+                "per_rank_kernel_step_draw_ms": per_rank,
                 "e2e": e2e_line,
                 "gpu_launches": int(launches),
                 "clocks": clocks,

@@ -29,6 +29,23 @@ namespace rt {
 // around the image centre and the cheapest (background outside the box) at its edges; in row-major
 // order the last rows start when the frame is almost done and their long blocks run alone.
 // Starting tiles centre-out removes that tail (60 us of a 355 us 1080p frame).
+// A launch-order table sorted by distance keeps mirror-image tiles next to each other, always in the same order (left
+// before right, top before bottom), so an N-way interleave would hand one rank the same side of every ring — and the
+// sides of the box do not cost the same.  Shuffling inside short windows keeps the overall order (expensive first)
+// and decorrelates the deal from the geometry.  Deterministic: every rank builds the same table.
+static void shuffle_windows(std::vector<int> &order, size_t begin, size_t end, size_t window = 32) {
+  for (size_t w0 = begin; w0 < end; w0 += window) {
+    const size_t w1 = std::min(end, w0 + window);
+    uint32_t s = (uint32_t)(w0 * 2654435761u) ^ 0x9e3779b9u;
+    for (size_t i = w1 - 1; i > w0; i--) {
+      s ^= s << 13;
+      s ^= s >> 17;
+      s ^= s << 5;
+      std::swap(order[i], order[w0 + s % (uint32_t)(i - w0 + 1)]);
+    }
+  }
+}
+
 // Four lanes per pixel pay off when the launch cannot fill the GPU for long: its duration is then set by its slowest
 // blocks, the tiles whose pixels run mirror / glass bounce chains.  kSplitHeavy (mixed launch) splits only those tiles.
 // RT_FLAG_SPLIT_PIXELS / RT_FLAG_SPLIT_HEAVY / RT_FLAG_NO_SPLIT force a mode; default: by the size of the launch.
@@ -52,16 +69,11 @@ SplitMode split_mode(const rt_ctx *ctx, const FrameParams &fp) {
 // point P lies on the ray through (vx, vy) = f (w.x, w.y) / w.z with w = R^-1 (P - cam).  The hull of the projected
 // corners contains the projection of the box as long as all corners are in front of the camera; otherwise (or if R is
 // singular) the rectangle is the whole frame.  Two pixels of margin absorb the rounding of this float arithmetic.
-void visible_rect(const rt_ctx *ctx, FrameParams &fp) {
-  fp.vis_x0 = 0;
-  fp.vis_y0 = 0;
-  fp.vis_x1 = fp.W;
-  fp.vis_y1 = fp.H;
+static bool inverse_rotation(const FrameParams &fp, double inv[9]) {
   const float *m = fp.rot;
   const double det = (double)m[0] * (m[4] * m[8] - m[5] * m[7]) - (double)m[1] * (m[3] * m[8] - m[5] * m[6]) +
                      (double)m[2] * (m[3] * m[7] - m[4] * m[6]);
-  if (!(fabs(det) > 1e-6) || !(fp.focal > 0.0f)) return;
-  double inv[9];
+  if (!(fabs(det) > 1e-6) || !(fp.focal > 0.0f)) return false;
   inv[0] = (m[4] * m[8] - m[5] * m[7]) / det;
   inv[1] = (m[2] * m[7] - m[1] * m[8]) / det;
   inv[2] = (m[1] * m[5] - m[2] * m[4]) / det;
@@ -71,17 +83,36 @@ void visible_rect(const rt_ctx *ctx, FrameParams &fp) {
   inv[6] = (m[3] * m[7] - m[4] * m[6]) / det;
   inv[7] = (m[1] * m[6] - m[0] * m[7]) / det;
   inv[8] = (m[0] * m[4] - m[1] * m[3]) / det;
+  return true;
+}
+
+// pixel position (fractional) of the world point cam + P_rel seen through the camera; false if beside / behind it
+static bool project_point(const FrameParams &fp, const double inv[9], const double P[3], double *px, double *py, double *depth) {
+  const double wx = inv[0] * P[0] + inv[1] * P[1] + inv[2] * P[2], wy = inv[3] * P[0] + inv[4] * P[1] + inv[5] * P[2],
+               wz = inv[6] * P[0] + inv[7] * P[1] + inv[8] * P[2];
+  if (!(wz > 1e-3)) return false;
+  const double vx = fp.focal * wx / wz, vy = fp.focal * wy / wz;  // virtual (sub-pixel) coordinates, kernels.cl:384-400
+  *px = (vx + 0.5 * fp.W * fp.A) / fp.A;
+  *py = (vy + 0.5 * fp.H * fp.A) / fp.A;
+  if (depth) *depth = wz;
+  return true;
+}
+
+void visible_rect(const rt_ctx *ctx, FrameParams &fp) {
+  fp.vis_x0 = 0;
+  fp.vis_y0 = 0;
+  fp.vis_x1 = fp.W;
+  fp.vis_y1 = fp.H;
+  double inv[9];
+  if (!inverse_rotation(fp, inv)) return;
   double x0 = 1e300, y0 = 1e300, x1 = -1e300, y1 = -1e300;
   for (int c = 0; c < 8; c++) {
     const double P[3] = {(c & 1 ? ctx->scene_hi[0] : ctx->scene_lo[0]) - (double)fp.cam[0],
                          (c & 2 ? ctx->scene_hi[1] : ctx->scene_lo[1]) - (double)fp.cam[1],
                          (c & 4 ? ctx->scene_hi[2] : ctx->scene_lo[2]) - (double)fp.cam[2]};
     if (!(fabs(P[0]) < 1e30 && fabs(P[1]) < 1e30 && fabs(P[2]) < 1e30)) return;
-    const double wx = inv[0] * P[0] + inv[1] * P[1] + inv[2] * P[2], wy = inv[3] * P[0] + inv[4] * P[1] + inv[5] * P[2],
-                 wz = inv[6] * P[0] + inv[7] * P[1] + inv[8] * P[2];
-    if (!(wz > 1e-3)) return;  // a corner beside or behind the camera: no bound
-    const double vx = fp.focal * wx / wz, vy = fp.focal * wy / wz;  // virtual (sub-pixel) coordinates, kernels.cl:384-400
-    const double px = (vx + 0.5 * fp.W * fp.A) / fp.A, py = (vy + 0.5 * fp.H * fp.A) / fp.A;
+    double px, py;
+    if (!project_point(fp, inv, P, &px, &py, nullptr)) return;  // a corner beside or behind the camera: no bound
     x0 = fmin(x0, px);
     x1 = fmax(x1, px);
     y0 = fmin(y0, py);
@@ -143,6 +174,25 @@ bool mixed_tables_for(rt_ctx *ctx, const FrameParams &fp, cudaStream_t stream, c
     const int sgx = (fp.W + kSplitTileW - 1) / kSplitTileW;
     const float cx = 0.5f * (float)fp.W, cy = 0.5f * (float)fp.H;
     std::vector<std::pair<float, int>> lt, st;
+    // The split sub-tiles start in order of expected cost — distance from the nearest sphere's projected centre, in
+    // units of its projected radius (the bounce chains are longest through the middle of the glass sphere) — so that
+    // the interleave deals the expensive ones evenly over the ranks and none of them is left for the end.
+    double sph[RT_SPHERES][3];
+    int n_sph = 0;
+    {
+      double inv[9];
+      if (inverse_rotation(fp, inv))
+        for (int i = 0; i < RT_SPHERES; i++) {
+          const double P[3] = {(double)rt::kSphereCenterR2[i][0] - fp.cam[0], (double)rt::kSphereCenterR2[i][1] - fp.cam[1],
+                               (double)rt::kSphereCenterR2[i][2] - fp.cam[2]};
+          double px, py, depth;
+          if (!project_point(fp, inv, P, &px, &py, &depth)) continue;
+          sph[n_sph][0] = px;
+          sph[n_sph][1] = py;
+          sph[n_sph][2] = fmax(1.0, sqrt((double)rt::kSphereCenterR2[i][3]) * fp.focal / depth / fp.A);  // radius in pixels
+          n_sph++;
+        }
+    }
     for (int by = 0; by < gy; by++)
       for (int bx = 0; bx < gx; bx++) {
         const int tx = bx * kTileW, ty = fp.row0 + by * kTileH;
@@ -155,8 +205,19 @@ bool mixed_tables_for(rt_ctx *ctx, const FrameParams &fp, cudaStream_t stream, c
           for (int sx = 0; sx < kTileW / kSplitTileW; sx++) {
             const int px = tx + sx * kSplitTileW, py = ty + sy * kSplitTileH;
             if (px >= fp.W || py >= fp.row0 + fp.rows) continue;
-            const float x = (float)(px + kSplitTileW / 2) - cx, y = (float)(py + kSplitTileH / 2) - cy;
-            st.emplace_back(x * x + y * y, (by * (kTileH / kSplitTileH) + sy) * sgx + bx * (kTileW / kSplitTileW) + sx);
+            float cost_key = 0.0f;
+            if (n_sph == 0) {
+              const float x = (float)(px + kSplitTileW / 2) - cx, y = (float)(py + kSplitTileH / 2) - cy;
+              cost_key = x * x + y * y;
+            } else {
+              double best = 1e300;
+              for (int i = 0; i < n_sph; i++) {
+                const double dx = (px + kSplitTileW / 2) - sph[i][0], dy = (py + kSplitTileH / 2) - sph[i][1];
+                best = fmin(best, sqrt(dx * dx + dy * dy) / sph[i][2] + (i == 0 ? 0.0 : 0.5));  // sphere 0 is the glass one
+              }
+              cost_key = (float)best;
+            }
+            st.emplace_back(cost_key, (by * (kTileH / kSplitTileH) + sy) * sgx + bx * (kTileW / kSplitTileW) + sx);
           }
       }
     std::sort(lt.begin(), lt.end());
@@ -165,6 +226,8 @@ bool mixed_tables_for(rt_ctx *ctx, const FrameParams &fp, cudaStream_t stream, c
     both.reserve(lt.size() + st.size() + 1);
     for (const auto &e : lt) both.push_back(e.second);
     for (const auto &e : st) both.push_back(e.second);
+    shuffle_windows(both, 0, lt.size());
+    shuffle_windows(both, lt.size(), lt.size() + st.size());
     both.push_back(0);
     // a frame in flight (on any stream of this context) may still be reading the tables this slot held
     if (m.valid && cudaDeviceSynchronize() != cudaSuccess) {
@@ -215,6 +278,7 @@ const int *tile_order_for(rt_ctx *ctx, int row0, int rows, int grid_x, int n_blo
   std::sort(key.begin(), key.end());
   std::vector<int> order((size_t)n_blocks);
   for (int b = 0; b < n_blocks; b++) order[(size_t)b] = key[(size_t)b].second;
+  shuffle_windows(order, 0, order.size());
   int *d = nullptr;
   if (cudaMalloc(&d, sizeof(int) * (size_t)(n_blocks ? n_blocks : 1)) != cudaSuccess) {
     cudaGetLastError();
