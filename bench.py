@@ -371,7 +371,7 @@ def run_ours(args, cfg) -> int:
         def render_only():
             fno[0] += 1
             if gather == "p2p" and rank != 0:
-                r.peer_wait(consumed_flag, 1, fno[0] - 1, sptr)  # rank 0 is done with the previous frame
+                r.gate_next_frame(consumed_flag, fno[0] - 1)  # rank 0 is done with the previous frame (checked inside the draw kernel)
             r.render_device(rot, cam4, light4, cfg.focal, dev_ptr=(0 if _DEBUG_LOCAL_STORES else target), stream=sptr)
 
         def gather_only(consume=True):

@@ -200,6 +200,11 @@ int rt_ipc_close_frame(rt_ctx *ctx, uint32_t *dev_argb);
 uint32_t *rt_peer_flags(rt_ctx *ctx);
 int rt_peer_signal(rt_ctx *ctx, uint32_t *dev_flag, uint32_t value, void *stream);
 int rt_peer_wait(rt_ctx *ctx, const uint32_t *dev_flags, int n, uint32_t value, void *stream);
+/* The same wait folded into the next draw launch of this context (rt_render_device): none of its pixels is stored
+ * before *dev_flag >= value.  Cheaper than rt_peer_wait in front of the launch — no extra kernel; each block checks
+ * a device-local copy of the flag and only the first ones poll the owner's memory.  One launch, then cleared.
+ * No reference counterpart (the reference has one device and one in-order queue, skeleton.cpp:388). */
+int rt_gate_next_frame(rt_ctx *ctx, const uint32_t *dev_flag, uint32_t value);
 
 /* Blocking read-back of the WHOLE frame buffer of this context (width*height uint32) — what the
  * owner of a peer-written frame calls once the peers are done. */

@@ -67,6 +67,7 @@ RT_SYMBOLS = {
     "rt_peer_flags": (ctypes.c_void_p, [ctypes.c_void_p]),
     "rt_peer_signal": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_uint32, ctypes.c_void_p]),
     "rt_peer_wait": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_uint32, ctypes.c_void_p]),
+    "rt_gate_next_frame": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_uint32]),
     "rt_read_frame": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p]),
     "rt_version": (ctypes.c_char_p, []),
 }

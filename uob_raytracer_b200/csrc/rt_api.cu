@@ -324,6 +324,7 @@ static int free_ctx(rt_ctx *ctx) {
   if (ctx->d_scene) cudaFree(ctx->d_scene);
   if (ctx->d_ray_counters) cudaFree(ctx->d_ray_counters);
   if (ctx->d_wait_status) cudaFree(ctx->d_wait_status);
+  if (ctx->d_gate_seen) cudaFree(ctx->d_gate_seen);
   for (auto &t : ctx->tile_orders) cudaFree(t.d_order);
   rt::bvh_free(ctx);
   for (int b = 0; b < rt_ctx::kBands; b++) {
@@ -417,6 +418,8 @@ rt_ctx *rt_create(const rt_config *cfg) {
   // the frame, followed by RT_PEER_FLAGS hand-over flags (same allocation, so one IPC handle maps both)
   const size_t frame_words = (size_t)cfg->width * cfg->height + RT_PEER_FLAGS;
   if ((e = cudaMalloc(&ctx->d_frame, sizeof(uint32_t) * frame_words)) != cudaSuccess) return fail("creating screen buffer", e);
+  if ((e = cudaMalloc(&ctx->d_gate_seen, sizeof(uint32_t))) != cudaSuccess) return fail("creating gate flag copy", e);
+  if ((e = cudaMemsetAsync(ctx->d_gate_seen, 0, sizeof(uint32_t), ctx->stream)) != cudaSuccess) return fail("clearing gate flag copy", e);
   if ((e = cudaMalloc(&ctx->d_wait_status, sizeof(int))) != cudaSuccess) return fail("creating wait status", e);
   if ((e = cudaMemsetAsync(ctx->d_wait_status, 0, sizeof(int), ctx->stream)) != cudaSuccess) return fail("clearing wait status", e);
   if (cfg->flags & RT_FLAG_COUNT_RAYS) {
@@ -570,6 +573,28 @@ static int render_impl(rt_ctx *ctx, const float rot12[12], const float cam[4], c
     fp.light[c] = light[c];
   }
   rt::visible_rect(ctx, fp);
+  // frame gate: the tuned brute-force kernels poll the flag themselves; the other kernels get a wait kernel in front
+  fp.gate_flag = nullptr;
+  fp.gate_value = 0;
+  fp.gate_seen = ctx->d_gate_seen;
+  fp.gate_status = ctx->d_wait_status;
+  if (ctx->gate_flag) {
+    const bool in_kernel = !ctx->use_bvh && !ctx->d_ray_counters &&
+                           !((ctx->cfg.flags & RT_FLAG_STRICT_IEEE) && (ctx->cfg.flags & RT_FLAG_REFERENCE_LOOPS));
+    if (in_kernel) {
+      if (ctx->gate_flag != ctx->gate_flag_cached) {  // the device-local copy belongs to another flag
+        RT_CUDA(ctx, cudaMemsetAsync(ctx->d_gate_seen, 0, sizeof(uint32_t), stream), "clearing gate flag copy");
+        ctx->gate_flag_cached = ctx->gate_flag;
+      }
+      fp.gate_flag = ctx->gate_flag;
+      fp.gate_value = ctx->gate_value;
+    } else {
+      RT_CUDA(ctx, rt::launch_peer_wait(ctx->gate_flag, 1, ctx->gate_value, ctx->d_wait_status, stream), "enqueueing frame gate");
+      ctx->launches++;
+    }
+    ctx->peer_waits = true;
+    ctx->gate_flag = nullptr;
+  }
   fp.out = dev_argb ? dev_argb : ctx->d_frame;
   fp.ray_counters = ctx->d_ray_counters;
   if (ctx->d_ray_counters && band_row0 < 0)
@@ -806,6 +831,13 @@ int rt_peer_wait(rt_ctx *ctx, const uint32_t *dev_flags, int n, uint32_t value, 
           "enqueueing peer wait");
   ctx->launches++;
   ctx->peer_waits = true;
+  return RT_OK;
+}
+
+int rt_gate_next_frame(rt_ctx *ctx, const uint32_t *dev_flag, uint32_t value) {
+  if (!ctx || !dev_flag) return RT_ERR_INVALID;
+  ctx->gate_flag = dev_flag;
+  ctx->gate_value = value;
   return RT_OK;
 }
 

@@ -25,6 +25,30 @@ __device__ __forceinline__ void draw_fast_body(const FrameParams &p, const float
   __shared__ int s_spheres_visible;
   __shared__ int s_wlist[kThreads / 32][kWarpListMax];  // per-warp shadow caster lists
 
+  if (p.gate_flag) {
+    // Frame gate (rt_gate_next_frame): the frame buffer may belong to another GPU that is still reading the previous
+    // frame.  One thread per block checks the device-local copy of the flag, and only polls the owner's memory over
+    // NVLink while that copy is behind; the barrier orders every store of the block after the acquire.
+    if (threadIdx.x == 0) {
+      uint32_t seen;
+      asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(p.gate_seen) : "memory");
+      if ((int32_t)(seen - p.gate_value) < 0) {
+        const long long t0 = clock64();
+        for (;;) {
+          uint32_t v;
+          asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p.gate_flag) : "memory");
+          if ((int32_t)(v - p.gate_value) >= 0) break;
+          if (clock64() - t0 > 4000000000ll) {  // ~2 s: give up instead of hanging the GPU (reported by rt_synchronize)
+            atomicExch(p.gate_status, 1);
+            break;
+          }
+          __nanosleep(100);
+        }
+        atomicMax(p.gate_seen, p.gate_value);
+      }
+    }
+    __syncthreads();
+  }
   int x, y, tile_x, tile_y;
   const bool in_frame = pixel_of_thread<SPLIT>(p, block, order, grid_x, x, y, tile_x, tile_y);
   constexpr int kTW = SPLIT ? kSplitTileW : kTileW, kTH = SPLIT ? kSplitTileH : kTileH;

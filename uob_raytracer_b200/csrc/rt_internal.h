@@ -46,6 +46,10 @@ struct rt_ctx {
   int sm_count = 0;
   uint64_t launches = 0;
   unsigned long long *d_ray_counters = nullptr;  // RT_FLAG_COUNT_RAYS
+  const uint32_t *gate_flag = nullptr;           // rt_gate_next_frame: applies to the next draw launch, then cleared
+  uint32_t gate_value = 0;
+  const uint32_t *gate_flag_cached = nullptr;    // the flag d_gate_seen mirrors
+  uint32_t *d_gate_seen = nullptr;
   int *d_wait_status = nullptr;                  // set by a rt_peer_wait kernel that timed out
   bool peer_waits = false;
   size_t launch_extra_smem = 0;

@@ -23,6 +23,12 @@ struct FrameParams {
   // pixel rectangle [vis_x0, vis_x1) x [vis_y0, vis_y1) outside which no primary ray can hit anything (projection of the
   // scene's bounding box, rt_api.cu): tiles outside it are black without looking at the scene
   int vis_x0, vis_y0, vis_x1, vis_y1;
+  // rt_gate_next_frame: no pixel of this launch is stored before *gate_flag >= gate_value (another GPU's "I have consumed
+  // the previous frame" flag).  gate_seen is a device-local copy of the last value observed, gate_status the time-out flag.
+  const uint32_t *gate_flag;
+  uint32_t gate_value;
+  uint32_t *gate_seen;
+  int *gate_status;
   int A, S, B;     // AA edge, shadow samples, max bounces
   float focal;
   float rot[9];    // rows r0, r1, r2 (skeleton.cpp:149-151)

@@ -161,6 +161,10 @@ class Renderer:
     def peer_wait(self, flags_ptr: int, n: int, value: int, stream: int = 0) -> None:
         self._check(self._lib.rt_peer_wait(self._ctx, flags_ptr, n, value, stream or None))
 
+    def gate_next_frame(self, flag_ptr: int, value: int) -> None:
+        """The next render_device stores no pixel before *flag_ptr >= value (the wait folded into the draw kernel)."""
+        self._check(self._lib.rt_gate_next_frame(self._ctx, flag_ptr, value))
+
     def set_stream(self, stream: int) -> None:
         """Use the caller's cudaStream_t (0 = back to the context's own) for everything that follows."""
         self._check(self._lib.rt_set_stream(self._ctx, stream or None))
