@@ -556,7 +556,7 @@ def run_ours(args, cfg) -> int:
                 "e2e": e2e_line,
                 "gpu_launches": int(launches),
                 "clocks": clocks,
-                "roofline": {"bound": "fp32", "kernel": "draw_fast_kernel<%d,true>" % (10 if cfg.shadow_samples % 10 == 0 else 8),
+                "roofline": {"bound": "fp32", "kernel": "draw_fast_kernel<%d,true,false,false>" % (10 if cfg.shadow_samples % 10 == 0 else 8),
                              "achieved": round(achieved, 3), "peak": round(fp32_peak, 3), "unit": "TFLOP/s",
                              "frac": round(achieved / fp32_peak, 4) if fp32_peak else None,
                              "peak_source": "FFMA microbenchmark in this run (rt_measure_fp32_peak); MEASURED_PEAKS.json has no FP32 entry",
