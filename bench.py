@@ -203,17 +203,16 @@ def cpu_reference_frame(cfg, rows_step: int, threads: int = 0, speed: bool = Fal
     import uob_raytracer_b200 as u
     scene, rot, cam4, light4 = scene_and_camera(cfg.name)
     if cfg.name == "cfg4":
-        # Brute force over 1.3 M triangles costs ~25 ms per ray per core, so the CPU sample is ONE row through the
-        # mesh of the same scene and camera at quarter resolution (480x270, focal scaled): ~20 k rays, ~30 s on 16 cores.
+        # Brute force over 1.3 M triangles costs ~25 ms per ray per core, so the CPU sample is the same scene and camera
+        # at 1/64 resolution (30x16 pixels, focal scaled; one row per host thread): ~17 k rays, ~30 s on 16 cores.
         from uob_raytracer_b200.configs import RenderConfig
-        small = RenderConfig("cfg4-sample", cfg.width // 4, cfg.height // 4, cfg.aa, cfg.shadow_samples, cfg.max_bounces, "")
-        y0 = small.height // 2
-        rays = gpu_ray_counts(small, scene, rot, cam4, light4, row0=y0, rows=1)["rays"]
+        small = RenderConfig("cfg4-sample", cfg.width // 64, cfg.height // 64, cfg.aa, cfg.shadow_samples, cfg.max_bounces, "")
+        rays = gpu_ray_counts(small, scene, rot, cam4, light4)["rays"]
         t0 = time.perf_counter()
         kind = "reference" if ob.ref_available(cfg.aa, cfg.shadow_samples, cfg.max_bounces) else "port"
         fn = ob.ref_render if kind == "reference" else ob.oracle_render
         fn(small.width, small.height, small.aa, small.shadow_samples, small.max_bounces, small.focal, scene.verts, scene.normals,
-           scene.colors, rot, cam4, light4, y0=y0, y1=y0 + 1, threads=threads)
+           scene.colors, rot, cam4, light4, threads=threads)
         return time.perf_counter() - t0, rays, kind
     counts = load_counts(cfg.name)
     if rows_step == 1:
