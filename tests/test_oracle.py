@@ -148,3 +148,45 @@ def test_light_sequence(ob):
     assert xs[0] == np.float32(-0.025) and xs.min() >= -0.5 and xs.max() <= 0.5
     # it turns round: goes left first, later comes back right of its start
     assert xs[:50].min() < -0.4 and xs.max() > 0.4
+
+
+def test_opencl_reference_library_carries_the_unmodified_kernel_text(ob):
+    """oracle/_ref/libref_ocl.so (the reference kernel for NVIDIA's OpenCL driver on the GPU box) embeds kernels.cl
+    verbatim; other configs only substitute the reference's own parameter tokens.  No OpenCL call is made here."""
+    import os
+    if not ob.ref_ocl_available():
+        pytest.skip("oracle/_ref/libref_ocl.so not built (run oracle/build_ref.py where /root/reference exists)")
+    text = ob.ref_ocl_source()
+    assert "kernel void draw(" in text.replace("__kernel", "kernel") and "light_sources = 10" in text
+    ref = "/root/reference/Source/kernels.cl"
+    if os.path.exists(ref):
+        with open(ref) as f:
+            want = f.read().replace("\r", "")
+        assert text.rstrip("\n") == want.rstrip("\n")
+    cfg2 = ob.ref_ocl_source(2, 8, 10, 1920, 1080)
+    changed = [(a, b) for a, b in zip(text.split("\n"), cfg2.split("\n")) if a != b]
+    assert len(text.split("\n")) == len(cfg2.split("\n")) and len(changed) == 3  # width, height, shadow samples
+    assert all(("SCREEN_" in a) or ("light_sources" in a) for a, _ in changed)
+    cfg3 = ob.ref_ocl_source(4, 10, 4, 3840, 2160)
+    assert "rays_x = 4;" in cfg3 and "#define aa_rays 16" in cfg3 and "const int bounces = 4;" in cfg3
+    # with no OpenCL platform in this container the call reports an error instead of crashing
+    import uob_raytracer_b200 as u
+    sc, cam = u.load_test_model(), u.Camera()
+    try:
+        ob.ref_ocl_render(128, 4, 2, 10, 10, 100.0, sc.verts, sc.normals, sc.colors, cam.rot(), cam.position, cam.light, frames=1)
+    except RuntimeError as e:
+        assert "OpenCL" in str(e)
+
+
+def test_speed_build_of_the_reference_is_a_different_rounding_not_a_different_image(ob, golden_scene):
+    """The -O3/AVX2/FMA build that bench.py times as cpu_baseline.speed_build: same image within the north-star
+    tolerance, not bit-identical (which is why parity always uses the strict build)."""
+    if not ob.ref_speed_available(2, 10, 10):
+        pytest.skip("speed build missing or this CPU lacks AVX2/FMA")
+    from conftest import assert_within_tolerance
+    v, n, c = golden_scene
+    rot = ob.oracle_rot_matrix(0.0, 0.0)
+    args = (160, 120, 2, 10, 10, 1100.0 * 2 * 120 / 1024, v, n, c, rot, [0, 0, -3.2], [0, -0.5, -0.7])
+    strict = ob.ref_render(*args)
+    fast = ob.ref_render(*args, speed=True)
+    assert_within_tolerance(fast, strict, "speed build vs strict build")
