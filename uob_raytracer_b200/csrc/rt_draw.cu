@@ -1,7 +1,8 @@
 // rt_draw.cu — the `draw` kernel (Source/kernels.cl:368-428) for sm_100a,
 // brute-force variant: whole scene staged in shared memory, as the reference
 // does with async_work_group_copy into __local (kernels.cl:374-376).  This file holds the generic
-// (strict-IEEE) kernel and the dispatch; the fast kernels are in rt_draw_fast.cu.
+// kernel (the reference's plain loops: RT_FLAG_REFERENCE_LOOPS and RT_FLAG_COUNT_RAYS) and the dispatch;
+// the tuned kernels — fast and bit-exact — are in rt_draw_fast.cu.
 #include "rt_launch.cuh"
 
 namespace rt {
@@ -10,7 +11,7 @@ namespace rt {
 // and each row of the tile is one full 32-byte sector of the ARGB frame), a
 // block covers 16x16 pixels.
 // Generic kernel: one thread per pixel, reference loop structure (rt_brute.cuh).  Instantiated
-// with sfloat it is the RT_FLAG_STRICT_IEEE path.
+// with sfloat it is the un-culled anchor of the RT_FLAG_STRICT_IEEE path (RT_FLAG_REFERENCE_LOOPS).
 template <class T, int CH>
 __global__ void __launch_bounds__(kThreads) draw_brute_kernel(const __grid_constant__ FrameParams p, const float4 *__restrict__ scene,
                                                               int n, int n_sh) {

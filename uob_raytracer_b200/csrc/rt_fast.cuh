@@ -1,8 +1,10 @@
 // rt_fast.cuh — the fast arithmetic policy of the brute-force path, restructured
 // around what is shared between rays.  Same algorithm and same results as the
 // generic code in rt_brute.cuh up to floating-point rounding of the SHADING
-// (primary visibility is bit-identical, see below); the strict kernel stays the
-// bit-exact anchor.
+// (primary visibility is bit-identical, see below).  The culls are shared by
+// RT_FLAG_STRICT_IEEE (shadow_occ_strict / direct_light_strict at the end of this
+// file): there they only choose which tests are evaluated, the evaluation itself is
+// the reference's operation sequence and the frame stays bit-identical.
 //
 //  * Primary rays all start at the camera, so b = cam - v0, det[b,e1,e2] and the
 //    cofactors of det[-d,b,e2], det[-d,e1,b] are per-frame constants of each
@@ -36,6 +38,10 @@
 //
 //  * The mirror sphere's shadow test is skipped per point when the whole cone of
 //    jittered rays misses the sphere.
+//
+//  * Warp-level caster cull (box_may_be_shadowed_by): one caster list per warp from the bounding
+//    box of the warp's diffuse primary hits — plane bound over the box, and a beam cull against
+//    the cone frustum that contains every shadow ray from the box to the jittered light.
 #pragma once
 #include <type_traits>
 
