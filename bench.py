@@ -608,8 +608,8 @@ def run_ours(args, cfg) -> int:
                     if time.perf_counter() - t_budget > 15.0:
                         break
                 line["cpu_baseline"] = {
-                    "value": round(rays / best / 1e6, 2), "unit": UNIT, "cores": os.cpu_count(), "kind": kind,
-                    "sample": ("cfg4 scene at 480x270, one row through the mesh" if mesh else f"{cfg.name}, " + ("all rows" if step == 1 else f"every {step}th row")) +
+                    "value": float(f"{rays / best / 1e6:.4g}"), "unit": UNIT, "cores": os.cpu_count(), "kind": kind,
+                    "sample": ("cfg4 scene at 30x16 pixels (1/64 resolution, same camera), all rows" if mesh else f"{cfg.name}, " + ("all rows" if step == 1 else f"every {step}th row")) +
                               f", best of {i + 1} frames; verbatim kernels.cl via g++ shim (-O2, strict IEEE), all host threads",
                     "ms_per_frame": None if mesh else round(best * step * 1e3, 1)}
                 if not mesh:

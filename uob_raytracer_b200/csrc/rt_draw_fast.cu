@@ -425,7 +425,7 @@ __device__ __forceinline__ void draw_fast_body(const FrameParams &p, const float
 }
 
 template <int CH, bool SINGLE, bool STRICT, bool SPLIT>
-__global__ void __launch_bounds__(kThreads, STRICT ? 2 : RT_MINBLOCKS) draw_fast_kernel(const __grid_constant__ FrameParams p,
+__global__ void __launch_bounds__(kThreads, STRICT ? RT_STRICT_MINBLOCKS : RT_MINBLOCKS) draw_fast_kernel(const __grid_constant__ FrameParams p,
                                                                            const float4 *__restrict__ scene, int n, int n_sh) {
   draw_fast_body<CH, SINGLE, STRICT, SPLIT>(p, scene, n, n_sh, (int)blockIdx.x, p.tile_order, p.grid_x);
 }
@@ -435,7 +435,7 @@ __global__ void __launch_bounds__(kThreads, STRICT ? 2 : RT_MINBLOCKS) draw_fast
 // first n_split blocks of the grid; every other tile by an ordinary block.  The host classifies the tiles per camera
 // (rt_api.cu: mixed_tables_for); the classification only steers performance — either mapping renders any tile correctly.
 template <int CH, bool SINGLE, bool STRICT>
-__global__ void __launch_bounds__(kThreads, STRICT ? 2 : RT_MINBLOCKS) draw_fast_mixed_kernel(const __grid_constant__ FrameParams p,
+__global__ void __launch_bounds__(kThreads, STRICT ? RT_STRICT_MINBLOCKS : RT_MINBLOCKS) draw_fast_mixed_kernel(const __grid_constant__ FrameParams p,
                                                                                  const float4 *__restrict__ scene, int n, int n_sh) {
   if ((int)blockIdx.x < p.n_split)
     draw_fast_body<CH, SINGLE, STRICT, true>(p, scene, n, n_sh, (int)blockIdx.x, p.split_order, p.split_grid_x);

@@ -13,6 +13,9 @@ namespace rt {
 #ifndef RT_MINBLOCKS
 #define RT_MINBLOCKS 3
 #endif
+#ifndef RT_STRICT_MINBLOCKS  // the bit-exact kernels: 127 registers at 2 blocks per SM
+#define RT_STRICT_MINBLOCKS 2
+#endif
 constexpr int kThreads = RT_THREADS, kTileW = 16, kTileH = kThreads / 16;
 // SPLIT launches (four lanes per pixel, see rt_draw_fast.cu): a block covers 8 x 8 pixels, a warp 4 x 2
 constexpr int kSplitTileW = 8, kSplitTileH = kThreads / 4 / 8;
