@@ -67,7 +67,7 @@ struct rt_ctx {
     unsigned long long last_use = 0;
   };
   float scene_lo[3] = {0, 0, 0}, scene_hi[3] = {0, 0, 0};  // bounding box of the triangles and the two spheres
-  static constexpr int kMixedSlots = 8;
+  static constexpr int kMixedSlots = 16;
   MixedTables mixed[kMixedSlots];
   unsigned long long mixed_clock = 0;
   std::string err;
