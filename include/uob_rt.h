@@ -206,6 +206,18 @@ int rt_peer_wait(rt_ctx *ctx, const uint32_t *dev_flags, int n, uint32_t value, 
  * No reference counterpart (the reference has one device and one in-order queue, skeleton.cpp:388). */
 int rt_gate_next_frame(rt_ctx *ctx, const uint32_t *dev_flag, uint32_t value);
 
+/* Host-side launch planning, exposed for the CPU test suite (pure functions: no context, no device).  No reference
+ * counterpart — the reference launches one work-item per pixel over the whole frame (skeleton.cpp:170-172).
+ * rt_debug_visible_rect: the pixel rectangle {x0, y0, x1, y1} (half-open) outside which no primary ray of this camera
+ * can hit the box lo..hi; tiles outside it are written black without looking at the scene.
+ * rt_debug_tile_lists: the launch-order lists of a mixed launch for cfg (width, height, aa, row0, rows) and this camera:
+ * tiles[0..n_light) = row-major numbers of the ordinary 16x16 tiles, tiles[n_light..n_light+n_split) = numbers of the 8x8
+ * sub-tiles (on a grid ceil(width/8) wide) of the tiles that can see a sphere.  capacity = room in tiles[]. */
+int rt_debug_visible_rect(const rt_config *cfg, const float lo[3], const float hi[3], const float rot12[12], const float cam[4], float focal,
+                          int rect[4]);
+int rt_debug_tile_lists(const rt_config *cfg, const float rot12[12], const float cam[4], float focal, int *tiles, int capacity, int *n_light,
+                        int *n_split);
+
 /* Blocking read-back of the WHOLE frame buffer of this context (width*height uint32) — what the
  * owner of a peer-written frame calls once the peers are done. */
 int rt_read_frame(rt_ctx *ctx, uint32_t *host_argb);

@@ -68,6 +68,10 @@ RT_SYMBOLS = {
     "rt_peer_signal": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_uint32, ctypes.c_void_p]),
     "rt_peer_wait": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_uint32, ctypes.c_void_p]),
     "rt_gate_next_frame": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_uint32]),
+    "rt_debug_visible_rect": (ctypes.c_int, [ctypes.c_void_p, c_float_p, c_float_p, c_float_p, c_float_p, ctypes.c_float,
+                                             ctypes.POINTER(ctypes.c_int)]),
+    "rt_debug_tile_lists": (ctypes.c_int, [ctypes.c_void_p, c_float_p, c_float_p, ctypes.c_float, ctypes.POINTER(ctypes.c_int), ctypes.c_int,
+                                           ctypes.POINTER(ctypes.c_int), ctypes.POINTER(ctypes.c_int)]),
     "rt_read_frame": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p]),
     "rt_version": (ctypes.c_char_p, []),
 }

@@ -98,7 +98,10 @@ static bool project_point(const FrameParams &fp, const double inv[9], const doub
   return true;
 }
 
-void visible_rect(const rt_ctx *ctx, FrameParams &fp) {
+static void visible_rect_of(const float lo[3], const float hi[3], FrameParams &fp);
+void visible_rect(const rt_ctx *ctx, FrameParams &fp) { visible_rect_of(ctx->scene_lo, ctx->scene_hi, fp); }
+
+static void visible_rect_of(const float scene_lo[3], const float scene_hi[3], FrameParams &fp) {
   fp.vis_x0 = 0;
   fp.vis_y0 = 0;
   fp.vis_x1 = fp.W;
@@ -107,9 +110,8 @@ void visible_rect(const rt_ctx *ctx, FrameParams &fp) {
   if (!inverse_rotation(fp, inv)) return;
   double x0 = 1e300, y0 = 1e300, x1 = -1e300, y1 = -1e300;
   for (int c = 0; c < 8; c++) {
-    const double P[3] = {(c & 1 ? ctx->scene_hi[0] : ctx->scene_lo[0]) - (double)fp.cam[0],
-                         (c & 2 ? ctx->scene_hi[1] : ctx->scene_lo[1]) - (double)fp.cam[1],
-                         (c & 4 ? ctx->scene_hi[2] : ctx->scene_lo[2]) - (double)fp.cam[2]};
+    const double P[3] = {(c & 1 ? scene_hi[0] : scene_lo[0]) - (double)fp.cam[0], (c & 2 ? scene_hi[1] : scene_lo[1]) - (double)fp.cam[1],
+                         (c & 4 ? scene_hi[2] : scene_lo[2]) - (double)fp.cam[2]};
     if (!(fabs(P[0]) < 1e30 && fabs(P[1]) < 1e30 && fabs(P[2]) < 1e30)) return;
     double px, py;
     if (!project_point(fp, inv, P, &px, &py, nullptr)) return;  // a corner beside or behind the camera: no bound
@@ -158,6 +160,70 @@ static bool tile_may_see_sphere(const FrameParams &fp, int tile_x, int tile_y) {
   return false;
 }
 
+// Launch-order lists of a mixed launch (pure host code, also reached through rt_debug_tile_lists): `both` = the ordinary
+// 16x16 tiles that cannot see a sphere, then the 8x8 sub-tiles of those that can; returns the length of the first part.
+static size_t build_mixed_lists(const FrameParams &fp, std::vector<int> &both) {
+  const int gx = (fp.W + kTileW - 1) / kTileW, gy = (fp.rows + kTileH - 1) / kTileH;
+  const int sgx = (fp.W + kSplitTileW - 1) / kSplitTileW;
+  const float cx = 0.5f * (float)fp.W, cy = 0.5f * (float)fp.H;
+  std::vector<std::pair<float, int>> lt, st;
+  // The split sub-tiles start in order of expected cost — distance from the nearest sphere's projected centre, in
+  // units of its projected radius (the bounce chains are longest through the middle of the glass sphere) — so that
+  // the interleave deals the expensive ones evenly over the ranks and none of them is left for the end.
+  double sph[RT_SPHERES][3];
+  int n_sph = 0;
+  {
+    double inv[9];
+    if (inverse_rotation(fp, inv))
+      for (int i = 0; i < RT_SPHERES; i++) {
+        const double P[3] = {(double)rt::kSphereCenterR2[i][0] - fp.cam[0], (double)rt::kSphereCenterR2[i][1] - fp.cam[1],
+                             (double)rt::kSphereCenterR2[i][2] - fp.cam[2]};
+        double px, py, depth;
+        if (!project_point(fp, inv, P, &px, &py, &depth)) continue;
+        sph[n_sph][0] = px;
+        sph[n_sph][1] = py;
+        sph[n_sph][2] = fmax(1.0, sqrt((double)rt::kSphereCenterR2[i][3]) * fp.focal / depth / fp.A);  // radius in pixels
+        n_sph++;
+      }
+  }
+  for (int by = 0; by < gy; by++)
+    for (int bx = 0; bx < gx; bx++) {
+      const int tx = bx * kTileW, ty = fp.row0 + by * kTileH;
+      if (!tile_may_see_sphere(fp, tx, ty)) {
+        const float x = (float)(tx + kTileW / 2) - cx, y = (float)(ty + kTileH / 2) - cy;
+        lt.emplace_back(x * x + y * y, by * gx + bx);
+        continue;
+      }
+      for (int sy = 0; sy < kTileH / kSplitTileH; sy++)
+        for (int sx = 0; sx < kTileW / kSplitTileW; sx++) {
+          const int px = tx + sx * kSplitTileW, py = ty + sy * kSplitTileH;
+          if (px >= fp.W || py >= fp.row0 + fp.rows) continue;
+          float cost_key = 0.0f;
+          if (n_sph == 0) {
+            const float x = (float)(px + kSplitTileW / 2) - cx, y = (float)(py + kSplitTileH / 2) - cy;
+            cost_key = x * x + y * y;
+          } else {
+            double best = 1e300;
+            for (int i = 0; i < n_sph; i++) {
+              const double dx = (px + kSplitTileW / 2) - sph[i][0], dy = (py + kSplitTileH / 2) - sph[i][1];
+              best = fmin(best, sqrt(dx * dx + dy * dy) / sph[i][2] + (i == 0 ? 0.0 : 0.5));  // sphere 0 is the glass one
+            }
+            cost_key = (float)best;
+          }
+          st.emplace_back(cost_key, (by * (kTileH / kSplitTileH) + sy) * sgx + bx * (kTileW / kSplitTileW) + sx);
+        }
+    }
+  std::sort(lt.begin(), lt.end());
+  std::sort(st.begin(), st.end());
+  both.clear();
+  both.reserve(lt.size() + st.size() + 1);
+  for (const auto &e : lt) both.push_back(e.second);
+  for (const auto &e : st) both.push_back(e.second);
+  shuffle_windows(both, 0, lt.size());
+  shuffle_windows(both, lt.size(), lt.size() + st.size());
+  return lt.size();
+}
+
 bool mixed_tables_for(rt_ctx *ctx, const FrameParams &fp, cudaStream_t stream, const int **light, int *n_light, const int **split,
                       int *n_split) {
   float key[16] = {fp.rot[0], fp.rot[1], fp.rot[2], fp.rot[3], fp.rot[4], fp.rot[5], fp.rot[6], fp.rot[7], fp.rot[8],
@@ -170,64 +236,9 @@ bool mixed_tables_for(rt_ctx *ctx, const FrameParams &fp, cudaStream_t stream, c
   rt_ctx::MixedTables &m = hit ? *hit : *victim;
   m.last_use = ++ctx->mixed_clock;
   if (!hit) {
-    const int gx = (fp.W + kTileW - 1) / kTileW, gy = (fp.rows + kTileH - 1) / kTileH;
-    const int sgx = (fp.W + kSplitTileW - 1) / kSplitTileW;
-    const float cx = 0.5f * (float)fp.W, cy = 0.5f * (float)fp.H;
-    std::vector<std::pair<float, int>> lt, st;
-    // The split sub-tiles start in order of expected cost — distance from the nearest sphere's projected centre, in
-    // units of its projected radius (the bounce chains are longest through the middle of the glass sphere) — so that
-    // the interleave deals the expensive ones evenly over the ranks and none of them is left for the end.
-    double sph[RT_SPHERES][3];
-    int n_sph = 0;
-    {
-      double inv[9];
-      if (inverse_rotation(fp, inv))
-        for (int i = 0; i < RT_SPHERES; i++) {
-          const double P[3] = {(double)rt::kSphereCenterR2[i][0] - fp.cam[0], (double)rt::kSphereCenterR2[i][1] - fp.cam[1],
-                               (double)rt::kSphereCenterR2[i][2] - fp.cam[2]};
-          double px, py, depth;
-          if (!project_point(fp, inv, P, &px, &py, &depth)) continue;
-          sph[n_sph][0] = px;
-          sph[n_sph][1] = py;
-          sph[n_sph][2] = fmax(1.0, sqrt((double)rt::kSphereCenterR2[i][3]) * fp.focal / depth / fp.A);  // radius in pixels
-          n_sph++;
-        }
-    }
-    for (int by = 0; by < gy; by++)
-      for (int bx = 0; bx < gx; bx++) {
-        const int tx = bx * kTileW, ty = fp.row0 + by * kTileH;
-        if (!tile_may_see_sphere(fp, tx, ty)) {
-          const float x = (float)(tx + kTileW / 2) - cx, y = (float)(ty + kTileH / 2) - cy;
-          lt.emplace_back(x * x + y * y, by * gx + bx);
-          continue;
-        }
-        for (int sy = 0; sy < kTileH / kSplitTileH; sy++)
-          for (int sx = 0; sx < kTileW / kSplitTileW; sx++) {
-            const int px = tx + sx * kSplitTileW, py = ty + sy * kSplitTileH;
-            if (px >= fp.W || py >= fp.row0 + fp.rows) continue;
-            float cost_key = 0.0f;
-            if (n_sph == 0) {
-              const float x = (float)(px + kSplitTileW / 2) - cx, y = (float)(py + kSplitTileH / 2) - cy;
-              cost_key = x * x + y * y;
-            } else {
-              double best = 1e300;
-              for (int i = 0; i < n_sph; i++) {
-                const double dx = (px + kSplitTileW / 2) - sph[i][0], dy = (py + kSplitTileH / 2) - sph[i][1];
-                best = fmin(best, sqrt(dx * dx + dy * dy) / sph[i][2] + (i == 0 ? 0.0 : 0.5));  // sphere 0 is the glass one
-              }
-              cost_key = (float)best;
-            }
-            st.emplace_back(cost_key, (by * (kTileH / kSplitTileH) + sy) * sgx + bx * (kTileW / kSplitTileW) + sx);
-          }
-      }
-    std::sort(lt.begin(), lt.end());
-    std::sort(st.begin(), st.end());
     std::vector<int> both;
-    both.reserve(lt.size() + st.size() + 1);
-    for (const auto &e : lt) both.push_back(e.second);
-    for (const auto &e : st) both.push_back(e.second);
-    shuffle_windows(both, 0, lt.size());
-    shuffle_windows(both, lt.size(), lt.size() + st.size());
+    const size_t n_light_tiles = build_mixed_lists(fp, both);
+    const size_t n_split_tiles = both.size() - n_light_tiles;
     both.push_back(0);
     // a frame in flight (on any stream of this context) may still be reading the tables this slot held
     if (m.valid && cudaDeviceSynchronize() != cudaSuccess) {
@@ -253,8 +264,8 @@ bool mixed_tables_for(rt_ctx *ctx, const FrameParams &fp, cudaStream_t stream, c
       m.valid = false;
       return false;
     }
-    m.n_light = (int)lt.size();
-    m.n_split = (int)st.size();
+    m.n_light = (int)n_light_tiles;
+    m.n_split = (int)n_split_tiles;
     memcpy(m.key, key, sizeof key);
     m.valid = true;
   }
@@ -831,6 +842,48 @@ int rt_peer_wait(rt_ctx *ctx, const uint32_t *dev_flags, int n, uint32_t value, 
           "enqueueing peer wait");
   ctx->launches++;
   ctx->peer_waits = true;
+  return RT_OK;
+}
+
+static void debug_frame_params(const rt_config *cfg, const float rot12[12], const float cam[4], float focal, rt::FrameParams &fp) {
+  memset(&fp, 0, sizeof fp);
+  fp.W = cfg->width;
+  fp.H = cfg->height;
+  fp.row0 = cfg->row0;
+  fp.rows = cfg->rows > 0 ? cfg->rows : cfg->height - cfg->row0;
+  fp.A = cfg->aa;
+  fp.S = cfg->shadow_samples;
+  fp.B = cfg->max_bounces;
+  fp.focal = focal;
+  for (int r = 0; r < 3; r++)
+    for (int c = 0; c < 3; c++) fp.rot[3 * r + c] = rot12[4 * r + c];
+  for (int c = 0; c < 3; c++) fp.cam[c] = cam[c];
+}
+
+int rt_debug_visible_rect(const rt_config *cfg, const float lo[3], const float hi[3], const float rot12[12], const float cam[4], float focal,
+                          int rect[4]) {
+  if (!cfg || !lo || !hi || !rot12 || !cam || !rect) return RT_ERR_INVALID;
+  rt::FrameParams fp;
+  debug_frame_params(cfg, rot12, cam, focal, fp);
+  rt::visible_rect_of(lo, hi, fp);
+  rect[0] = fp.vis_x0;
+  rect[1] = fp.vis_y0;
+  rect[2] = fp.vis_x1;
+  rect[3] = fp.vis_y1;
+  return RT_OK;
+}
+
+int rt_debug_tile_lists(const rt_config *cfg, const float rot12[12], const float cam[4], float focal, int *tiles, int capacity, int *n_light,
+                        int *n_split) {
+  if (!cfg || !rot12 || !cam || !n_light || !n_split || capacity < 0 || (capacity > 0 && !tiles)) return RT_ERR_INVALID;
+  rt::FrameParams fp;
+  debug_frame_params(cfg, rot12, cam, focal, fp);
+  std::vector<int> both;
+  const size_t nl = rt::build_mixed_lists(fp, both);
+  *n_light = (int)nl;
+  *n_split = (int)(both.size() - nl);
+  if ((size_t)capacity < both.size()) return RT_ERR_INVALID;
+  for (size_t i = 0; i < both.size(); i++) tiles[i] = both[i];
   return RT_OK;
 }
 
