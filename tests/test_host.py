@@ -177,3 +177,20 @@ def test_parallel_obj_ingest_matches_reference_loader(ob, tmp_path):
     v, n, c = ob.ref_load_obj(str(p))
     assert s.n == 81920 == c.shape[0]
     assert s.verts.tobytes() == v.tobytes() and s.normals.tobytes() == n.tobytes() and s.colors.tobytes() == c.tobytes()
+
+
+def test_obj_number_spellings_match_reference_loader(ob, tmp_path):
+    """Spellings the fast path (std::from_chars) does not take itself — leading '+', exponent forms, tabs, indented
+    lines, CR line ends, extra tokens — still read as the reference's stream extractors read them: identical bytes."""
+    if not ob.ref_available():
+        pytest.skip("oracle/_ref/libref_scene.so not built")
+    txt = ("# odd but valid\nv 1 2 3\nv\t+1.5  -2.5e-1 .5\n  v 1e2 2E+1 3.\nvn 0 0 1\nvt 0 0\n"
+           "v 0.1000000015 123456.789e-3 -0\ng grp\nf 1 2 3\r\nf 2 3 4\nf   4 1\t2  \ns off\nf 3 1 4 2\n")
+    p = tmp_path / "q.obj"
+    p.write_text(txt)
+    s = u.load_obj(str(p))
+    v, n, c = ob.ref_load_obj(str(p))
+    assert s.n == 4
+    assert np.array_equal(s.verts.view(np.uint32), v.view(np.uint32))
+    assert np.array_equal(s.normals.view(np.uint32), n.view(np.uint32))
+    assert np.array_equal(s.colors.view(np.uint32), c.view(np.uint32))

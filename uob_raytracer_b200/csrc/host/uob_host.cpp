@@ -10,8 +10,15 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <fcntl.h>
+#include <sys/mman.h>
+#include <sys/stat.h>
+#include <unistd.h>
+
+#include <charconv>
 #include <functional>
 #include <string>
+#include <chrono>
 #include <thread>
 #include <unordered_map>
 #include <vector>
@@ -126,35 +133,82 @@ int flatten(const std::vector<Tri> &tris, float *verts, float *normals, float *c
 
 // OBJ reader with load_obj's semantics (Loader.cpp:27-56), built for meshes of a million faces.
 // The reference tokenises each line with operator>>; a line whose first token is exactly "v" or
-// "f" is used, everything else is skipped.  strtof/strtol give the same correctly-rounded values as
-// the stream extractors for well-formed numbers.  The file is read once, cut into one chunk per
+// "f" is used, everything else is skipped.  std::from_chars (and strtof/strtol for the spellings it does
+// not take: a leading '+', hex floats, out-of-range values) gives the same correctly-rounded values as
+// the stream extractors for well-formed numbers.  The file is mapped, cut into one chunk per
 // hardware thread at line boundaries, and every chunk is tokenised in parallel into its own vertex
 // and face lists; face indices are global (1-based over the whole file, as in the reference, which
 // also requires a vertex to precede the faces that use it), so triangles are built in a second
-// parallel pass once all vertices are known.
+// parallel pass once all vertices are known — straight into the flattened float4 arrays of
+// skeleton.cpp:474-484, which is what every caller wants.
 struct ObjChunk {
   std::vector<Vec4> vertices;
   std::vector<long> faces;  // 3 per face
   bool bad_face = false;
 };
 
+// a tokenised file: per-chunk face lists, all vertices, and where each chunk's vertices / faces start
+struct ParsedObj {
+  std::vector<ObjChunk> chunks;
+  std::vector<size_t> v_before, f_before;
+  Vec4 *vertices = nullptr;
+  size_t n = 0;  // faces
+  void clear() {
+    chunks.clear();
+    v_before.clear();
+    f_before.clear();
+    free(vertices);
+    vertices = nullptr;
+    n = 0;
+  }
+};
+
+inline bool obj_blank(char c) { return c == ' ' || c == '\t' || c == '\r'; }
+
+// strtof / strtol semantics on [p, eol): skip blanks, convert the longest valid prefix, return where it stopped
+// (p itself, with value 0, if nothing converts).  The slow path works on a NUL-terminated copy of the token, so
+// nothing ever reads past the mapped file.
+template <class T, class Slow> inline const char *obj_number(const char *p, const char *eol, T &out, Slow slow) {
+  while (p < eol && obj_blank(*p)) p++;
+  T v{};
+  const std::from_chars_result r = std::from_chars(p, eol, v);
+  if (r.ec == std::errc() && !(r.ptr < eol && (*r.ptr == 'x' || *r.ptr == 'X'))) {
+    out = v;
+    return r.ptr;
+  }
+  char tok[64];
+  size_t len = 0;
+  while (p + len < eol && len + 1 < sizeof tok && !obj_blank(p[len])) {
+    tok[len] = p[len];
+    len++;
+  }
+  tok[len] = '\0';
+  char *e = tok;
+  out = slow(tok, &e);
+  return p + (e - tok);
+}
+
 void parse_chunk(const char *p, const char *end, ObjChunk &out) {
+  const auto slow_f = [](const char *t, char **e) { return strtof(t, e); };
+  const auto slow_l = [](const char *t, char **e) { return strtol(t, e, 10); };
   while (p < end) {
     const char *eol = (const char *)memchr(p, '\n', (size_t)(end - p));
     if (!eol) eol = end;
     const char *q = p;
-    while (q < eol && (*q == ' ' || *q == '\t' || *q == '\r')) q++;
+    while (q < eol && obj_blank(*q)) q++;
     const char *tok = q;
-    while (q < eol && !(*q == ' ' || *q == '\t' || *q == '\r')) q++;
+    while (q < eol && !obj_blank(*q)) q++;
     if (q - tok == 1 && *tok == 'v') {
-      char *e;
-      const float x = strtof(q, &e);
-      const float y = strtof(e, &e);
-      const float z = strtof(e, &e);
+      float x = 0.f, y = 0.f, z = 0.f;
+      q = obj_number(q, eol, x, slow_f);
+      q = obj_number(q, eol, y, slow_f);
+      obj_number(q, eol, z, slow_f);
       out.vertices.push_back(Vec4{1.5f * x, 1.5f * y, 1.5f * z, 1.f});  // Loader.cpp:41
     } else if (q - tok == 1 && *tok == 'f') {
-      char *e;
-      const long a = strtol(q, &e, 10), b = strtol(e, &e, 10), c = strtol(e, &e, 10);
+      long a = 0, b = 0, c = 0;
+      q = obj_number(q, eol, a, slow_l);
+      q = obj_number(q, eol, b, slow_l);
+      obj_number(q, eol, c, slow_l);
       out.faces.push_back(a);
       out.faces.push_back(b);
       out.faces.push_back(c);
@@ -163,84 +217,161 @@ void parse_chunk(const char *p, const char *end, ObjChunk &out) {
   }
 }
 
-bool parse_obj(const char *path, std::vector<Tri> &tris) {
-  FILE *f = fopen(path, "rb");
-  if (!f) return false;
-  fseek(f, 0, SEEK_END);
-  const long size = ftell(f);
-  fseek(f, 0, SEEK_SET);
-  std::string buf((size_t)(size > 0 ? size : 0), '\0');
-  if (size > 0 && fread(&buf[0], 1, (size_t)size, f) != (size_t)size) {
-    fclose(f);
-    return false;
+// UOB_HOST_TRACE=1 prints where load_obj spends its time (stderr)
+struct PhaseTimer {
+  bool on = getenv("UOB_HOST_TRACE") != nullptr;
+  std::chrono::steady_clock::time_point t = std::chrono::steady_clock::now();
+  void lap(const char *what) {
+    if (!on) return;
+    const auto n = std::chrono::steady_clock::now();
+    fprintf(stderr, "uob_load_obj: %-18s %7.1f ms\n", what, std::chrono::duration<double, std::milli>(n - t).count());
+    t = n;
   }
-  fclose(f);
-  const char *base = buf.c_str(), *end = base + buf.size();
+};
+
+// the whole file in memory: mapped read-only, or read if it cannot be mapped
+struct FileBytes {
+  const char *data = nullptr;
+  size_t size = 0;
+  bool mapped = false;
+  std::string owned;
+  bool open(const char *path) {
+    const int fd = ::open(path, O_RDONLY);
+    if (fd < 0) return false;
+    struct stat st;
+    if (fstat(fd, &st) != 0 || !S_ISREG(st.st_mode)) {
+      ::close(fd);
+      return false;
+    }
+    size = (size_t)st.st_size;
+    if (size == 0) {
+      ::close(fd);
+      data = "";
+      return true;
+    }
+    void *m = mmap(nullptr, size, PROT_READ, MAP_PRIVATE | MAP_POPULATE, fd, 0);
+    if (m != MAP_FAILED) {
+      madvise(m, size, MADV_SEQUENTIAL);
+      data = (const char *)m;
+      mapped = true;
+      ::close(fd);
+      return true;
+    }
+    owned.resize(size);
+    size_t got = 0;
+    while (got < size) {
+      const ssize_t k = ::read(fd, &owned[got], size - got);
+      if (k <= 0) break;
+      got += (size_t)k;
+    }
+    ::close(fd);
+    if (got != size) return false;
+    data = owned.data();
+    return true;
+  }
+  ~FileBytes() {
+    if (mapped) munmap((void *)data, size);
+  }
+};
+
+unsigned host_threads(size_t work_bytes) {
   unsigned nt = std::thread::hardware_concurrency();
   if (nt < 1) nt = 1;
   if (nt > 64) nt = 64;
-  if (buf.size() < (1u << 20)) nt = 1;
+  if (work_bytes < (1u << 20)) nt = 1;
+  return nt;
+}
+
+template <class F> void run_parallel(unsigned nt, F fn) {
+  std::vector<std::thread> pool;
+  for (unsigned t = 1; t < nt; t++) pool.emplace_back(fn, t);
+  fn(0u);
+  for (auto &th : pool) th.join();
+}
+
+bool parse_obj(const char *path, ParsedObj &obj) {
+  PhaseTimer timer;
+  obj.clear();
+  FileBytes file;
+  if (!file.open(path)) return false;
+  timer.lap("map file");
+  const char *base = file.data, *end = base + file.size;
+  const unsigned nt = host_threads(file.size);
   // chunk boundaries at line starts
   std::vector<const char *> cut(nt + 1, end);
   cut[0] = base;
   for (unsigned t = 1; t < nt; t++) {
-    const char *p = base + buf.size() / nt * t;
+    const char *p = base + file.size / nt * t;
     const char *nl = (const char *)memchr(p, '\n', (size_t)(end - p));
     cut[t] = nl ? nl + 1 : end;
   }
-  std::vector<ObjChunk> chunks(nt);
-  {
-    std::vector<std::thread> pool;
-    for (unsigned t = 1; t < nt; t++) pool.emplace_back(parse_chunk, cut[t], cut[t + 1], std::ref(chunks[t]));
-    parse_chunk(cut[0], cut[1], chunks[0]);
-    for (auto &th : pool) th.join();
-  }
+  obj.chunks.resize(nt);
+  run_parallel(nt, [&](unsigned t) { parse_chunk(cut[t], cut[t + 1], obj.chunks[t]); });
+  timer.lap("tokenise");
   // vertices of the whole file, and for every chunk how many vertices precede it (a face may only
   // use vertices defined before it: Loader.cpp indexes the vector as it grows)
-  std::vector<size_t> v_before(nt + 1, 0), f_before(nt + 1, 0);
+  obj.v_before.assign(nt + 1, 0);
+  obj.f_before.assign(nt + 1, 0);
   for (unsigned t = 0; t < nt; t++) {
-    v_before[t + 1] = v_before[t] + chunks[t].vertices.size();
-    f_before[t + 1] = f_before[t] + chunks[t].faces.size() / 3;
+    obj.v_before[t + 1] = obj.v_before[t] + obj.chunks[t].vertices.size();
+    obj.f_before[t + 1] = obj.f_before[t] + obj.chunks[t].faces.size() / 3;
   }
-  std::vector<Vec4> vertices(v_before[nt]);
-  for (unsigned t = 0; t < nt; t++)
-    if (!chunks[t].vertices.empty()) memcpy(&vertices[v_before[t]], chunks[t].vertices.data(), sizeof(Vec4) * chunks[t].vertices.size());
-  tris.resize(f_before[nt]);
-  const Vec4 blue{0.0f, 0.2f, 0.4f, 0.5f};         // Loader.cpp:20
-  const Vec4 translate{-0.4f, 1.15f, -0.7f, 1.0f}; // Loader.cpp:48
-  auto build = [&](unsigned t) {
-    ObjChunk &ch = chunks[t];
+  obj.n = obj.f_before[nt];
+  if (obj.n > (size_t)INT_MAX) return false;
+  obj.vertices = (Vec4 *)malloc(sizeof(Vec4) * (obj.v_before[nt] ? obj.v_before[nt] : 1));
+  if (!obj.vertices) return false;
+  run_parallel(nt, [&](unsigned t) {
+    std::vector<Vec4> &v = obj.chunks[t].vertices;
+    if (!v.empty()) memcpy(obj.vertices + obj.v_before[t], v.data(), sizeof(Vec4) * v.size());
+    std::vector<Vec4>().swap(v);
+  });
+  // face indices are checked here, so that a bad file fails before the caller allocates anything
+  run_parallel(nt, [&](unsigned t) {
+    ObjChunk &ch = obj.chunks[t];
     // vertices visible to the faces of this chunk: all of the earlier chunks; inside the chunk the
     // interleaving of v and f lines is not tracked, so (conservatively, like the usual OBJ layout) the
     // chunk's own vertices count as well — an index beyond them is an error as in the reference
-    const long nv = (long)v_before[t + 1];
-    for (size_t k = 0; k < ch.faces.size() / 3; k++) {
-      const long a = ch.faces[3 * k], b = ch.faces[3 * k + 1], c = ch.faces[3 * k + 2];
-      if (a < 1 || b < 1 || c < 1 || a > nv || b > nv || c > nv) {
+    const long nv = (long)obj.v_before[t + 1];
+    for (long idx : ch.faces)
+      if (idx < 1 || idx > nv) {
         ch.bad_face = true;
         return;
       }
-      Tri tr{vertices[(size_t)a - 1], vertices[(size_t)b - 1], vertices[(size_t)c - 1], Vec4{0, 0, 0, 1}, blue};
-      compute_normal(tr);  // from the scaled, untransformed vertices; kept as is
-      Vec4 *vs[3] = {&tr.v1, &tr.v2, &tr.v0};
-      for (Vec4 *v : vs) {
-        v->x = (-1.f) * v->x + translate.x;
-        v->y = (-1.f) * v->y + translate.y;
-        v->z = (-1.f) * v->z + translate.z;
-        v->w = (-1.f) * v->w + translate.w;
-      }
-      tris[f_before[t] + k] = tr;
-    }
-  };
-  {
-    std::vector<std::thread> pool;
-    for (unsigned t = 1; t < nt; t++) pool.emplace_back(build, t);
-    build(0);
-    for (auto &th : pool) th.join();
-  }
+  });
+  timer.lap("gather + check");
   for (unsigned t = 0; t < nt; t++)
-    if (chunks[t].bad_face) return false;
+    if (obj.chunks[t].bad_face) return false;
   return true;
+}
+
+// Triangles of a tokenised file, flattened as skeleton.cpp:474-484 does, written by every host thread straight
+// into the caller's arrays (105 MB at a million faces).
+void build_triangles(const ParsedObj &obj, float *verts, float *normals, float *colors) {
+  const Vec4 blue{0.0f, 0.2f, 0.4f, 0.5f};         // Loader.cpp:20
+  const Vec4 translate{-0.4f, 1.15f, -0.7f, 1.0f}; // Loader.cpp:48
+  const unsigned nt = (unsigned)obj.chunks.size();
+  run_parallel(nt, [&](unsigned t) {
+    const ObjChunk &ch = obj.chunks[t];
+    for (size_t k = 0; k < ch.faces.size() / 3; k++) {
+      const long a = ch.faces[3 * k], b = ch.faces[3 * k + 1], c = ch.faces[3 * k + 2];
+      Tri tr{obj.vertices[(size_t)a - 1], obj.vertices[(size_t)b - 1], obj.vertices[(size_t)c - 1], Vec4{0, 0, 0, 1}, blue};
+      compute_normal(tr);  // from the scaled, untransformed vertices; kept as is
+      const Vec4 *vs[3] = {&tr.v0, &tr.v1, &tr.v2};
+      const size_t i = obj.f_before[t] + k;
+      float *o = verts + 12 * i;  // xyz of the three vertices after Loader.cpp:44-53, w = 0
+      for (const Vec4 *v : vs) {
+        o[0] = (-1.f) * v->x + translate.x;
+        o[1] = (-1.f) * v->y + translate.y;
+        o[2] = (-1.f) * v->z + translate.z;
+        o[3] = 0.0f;
+        o += 4;
+      }
+      const float nn[4] = {tr.normal.x, tr.normal.y, tr.normal.z, 0.0f};
+      memcpy(normals + 4 * i, nn, sizeof nn);
+      const float cc[4] = {blue.x, blue.y, blue.z, blue.w};
+      memcpy(colors + 4 * i, cc, sizeof cc);
+    }
+  });
 }
 
 void put_le32(unsigned char *p, uint32_t v) {
@@ -265,22 +396,27 @@ int uob_load_test_model(float *verts, float *normals, float *colors, int cap) {
 }
 
 int uob_load_obj(const char *path, float *verts, float *normals, float *colors, int cap) {
-  // the two-pass use (cap = 0 to size the buffers, then the real call) parses the file once
+  // the two-pass use (cap = 0 to size the buffers, then the real call) reads and tokenises the file once
   static thread_local std::string cached_path;
-  static thread_local std::vector<Tri> cached;
+  static thread_local ParsedObj cached;
   if (!path) return INT_MIN;
   if (cached_path != path || cap == 0) {
     cached.clear();
     cached_path.clear();
-    if (!parse_obj(path, cached)) return INT_MIN;
+    if (!parse_obj(path, cached)) {
+      cached.clear();
+      return INT_MIN;
+    }
     cached_path = path;
   }
-  const int rc = flatten(cached, verts, normals, colors, cap);
-  if (rc >= 0) {  // delivered: drop the copy
-    std::vector<Tri>().swap(cached);
-    cached_path.clear();
-  }
-  return rc;
+  if ((size_t)(cap < 0 ? 0 : cap) < cached.n || !verts || !normals || !colors) return -(int)cached.n;
+  PhaseTimer timer;
+  build_triangles(cached, verts, normals, colors);
+  timer.lap("build triangles");
+  const int n = (int)cached.n;
+  cached.clear();  // delivered: drop the tokens
+  cached_path.clear();
+  return n;
 }
 
 void uob_rot_matrix(float yaw, float pitch, float rot12[12]) {
