@@ -96,13 +96,12 @@ class ClockSampler:
 
     def _nvml_loop(self):
         nv, h = self.nvml, self.handle
-        while not self.stop_flag:
+        while not self.stop_flag:  # ~1-2 kHz; the short sleep keeps this thread off the GIL while the main thread launches frames
             try:
-                self.samples.append((nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM), nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM),
-                                     nv.nvmlDeviceGetPowerUsage(h) / 1000.0, nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)))
+                self.samples.append((nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM), nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)))
             except Exception:
                 pass
-            time.sleep(0.001)
+            time.sleep(0.0005)
 
     def start(self):
         # in-process NVML polling at ~1 kHz (a short timed region — 100 frames of 0.1 ms — ends before an nvidia-smi child
@@ -130,12 +129,23 @@ class ClockSampler:
         if self.nvml is not None:
             self.stop_flag = True
             self.thread.join(timeout=1.0)
+            nv, h = self.nvml, self.handle
+            source = "NVML, polled during the timed region"
+            if not self.samples:  # a timed region of a few ms can end before the first poll returns
+                try:
+                    self.samples.append((nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM), nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)))
+                    source = "NVML, one sample right at the end of the timed region (it was shorter than one poll)"
+                except Exception:
+                    pass
             bits = {"hw_slowdown": 0x8, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20, "sw_power_cap": 0x4}
             sm = [x[0] for x in self.samples]
-            reasons = sorted({k for x in self.samples for k, b in bits.items() if x[3] & b})
-            return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": float(max(x[1] for x in self.samples)) if sm else None,
-                    "power_w_max": round(max(x[2] for x in self.samples), 1) if sm else None, "samples": len(sm), "reasons": reasons,
-                    "source": "NVML, polled during the timed region"}
+            reasons = sorted({k for x in self.samples for k, b in bits.items() if x[1] & b})
+            try:
+                mx, power = float(nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)), round(nv.nvmlDeviceGetPowerUsage(h) / 1000.0, 1)
+            except Exception:
+                mx, power = None, None
+            return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx, "power_w": power, "samples": len(sm),
+                    "reasons": reasons, "source": source}
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         time.sleep(0.06)
