@@ -157,6 +157,12 @@ uint64_t rt_kernel_launches(const rt_ctx *ctx);
 /* "brute" or "bvh": which traversal rt_upload_scene selected. */
 const char *rt_scene_mode(const rt_ctx *ctx);
 
+/* Name of the draw kernel instantiation the last render call launched, e.g.
+ * "draw_fast_kernel<8,true,false,false>" (shadow chunk, S == chunk, strict, split) or "draw_fast_mixed_kernel<10,true,false>"
+ * — what bench.py prints as roofline.kernel and what the tests pin the benchmarked instantiation with.  "" before the
+ * first launch.  Diagnostic; no reference counterpart. */
+const char *rt_last_kernel_name(const rt_ctx *ctx);
+
 /* The reference never releases anything (no clRelease* anywhere); this does. */
 void rt_destroy(rt_ctx *ctx);
 
@@ -210,9 +216,9 @@ int rt_gate_next_frame(rt_ctx *ctx, const uint32_t *dev_flag, uint32_t value);
  * counterpart — the reference launches one work-item per pixel over the whole frame (skeleton.cpp:170-172).
  * rt_debug_visible_rect: the pixel rectangle {x0, y0, x1, y1} (half-open) outside which no primary ray of this camera
  * can hit the box lo..hi; tiles outside it are written black without looking at the scene.
- * rt_debug_tile_lists: the launch-order lists of a mixed launch for cfg (width, height, aa, row0, rows) and this camera:
- * tiles[0..n_light) = row-major numbers of the ordinary 16x16 tiles, tiles[n_light..n_light+n_split) = numbers of the 8x8
- * sub-tiles (on a grid ceil(width/8) wide) of the tiles that can see a sphere.  capacity = room in tiles[]. */
+ * rt_debug_tile_lists: what a mixed launch for cfg (width, height, aa, row0, rows) and this camera renders, in launch
+ * order: tiles[0..n_light) = row-major numbers of the ordinary 16x16 tiles, tiles[n_light..n_light+n_split) = numbers of
+ * the 8x8 sub-tiles (on a grid ceil(width/8) wide) of the tiles inside a sphere's screen rectangle.  capacity = room in tiles[]. */
 int rt_debug_visible_rect(const rt_config *cfg, const float lo[3], const float hi[3], const float rot12[12], const float cam[4], float focal,
                           int rect[4]);
 int rt_debug_tile_lists(const rt_config *cfg, const float rot12[12], const float cam[4], float focal, int *tiles, int capacity, int *n_light,

@@ -139,16 +139,25 @@ def test_mixed_launch_lists_cover_every_tile_once_and_split_what_sees_a_sphere(W
 
 
 def test_tile_lists_are_deterministic_and_deal_evenly():
-    """Every rank builds the tables on its own host: the result must not depend on anything but the inputs; an N-way
-    deal of the list (entries phase, phase + N, ...) gives every rank the same number of tiles +- 1."""
+    """Every rank plans the launch on its own host: the result must not depend on anything but the inputs.  The ranks of
+    an N-way interleave deal the split sub-tiles (entries phase, phase + N, ...: +- 1 each) and ALL tiles of the static
+    launch-order table, skipping those inside a sphere rectangle — so the ordinary tiles a rank really renders may differ
+    by a few between ranks, not more."""
     cfg = _cfg(1920, 1080, 2)
     a = _tile_lists(cfg, u.rot_matrix(), (0.0, 0.0, -3.2), 2320.3125)
     b = _tile_lists(cfg, u.rot_matrix(), (0.0, 0.0, -3.2), 2320.3125)
     assert (a[0] == b[0]).all() and (a[1] == b[1]).all()
-    for lst in a:
-        for n in (2, 4, 8):
-            sizes = [len(lst[p::n]) for p in range(n)]
-            assert max(sizes) - min(sizes) <= 1
+    assert 500 < len(a[1]) < 2500  # two spheres of ~110 px radius: some hundred tiles, not the frame
+    for n in (2, 4, 8):
+        sizes = [len(a[1][p::n]) for p in range(n)]
+        assert max(sizes) - min(sizes) <= 1
+    # the ordinary tiles: reconstruct the full launch-order table (ordinary tiles keep their relative order in it)
+    gx, gy = 120, 68
+    in_rect = np.ones(gx * gy, bool)
+    in_rect[a[0]] = False
+    # the table itself is not exported; any order that interleaves the rectangle tiles evenly deals evenly — check the
+    # worst case instead: rectangle tiles are < 6 % of the table, so no rank can lose more than that share
+    assert in_rect.mean() < 0.06
     # the side of the frame a rank gets is not tied to its phase: both halves of the frame in both phases of a 2-way deal
     gx = 120
     for p in range(2):

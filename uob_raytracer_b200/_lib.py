@@ -56,6 +56,7 @@ RT_SYMBOLS = {
     "rt_last_kernel_ms": (ctypes.c_float, [ctypes.c_void_p]),
     "rt_kernel_launches": (ctypes.c_uint64, [ctypes.c_void_p]),
     "rt_scene_mode": (ctypes.c_char_p, [ctypes.c_void_p]),
+    "rt_last_kernel_name": (ctypes.c_char_p, [ctypes.c_void_p]),
     "rt_destroy": (None, [ctypes.c_void_p]),
     "rt_last_error": (ctypes.c_char_p, [ctypes.c_void_p]),
     "rt_get_ray_counts": (ctypes.c_int, [ctypes.c_void_p, ctypes.POINTER(ctypes.c_uint64)]),

@@ -12,6 +12,8 @@
 //   skeleton_b200 [--frames N] [--width W --height H] [--aa A] [--shadow S] [--bounces B]
 //                 [--obj mesh.obj] [--gpus G] [--strict] [--pipeline] [--out screenshot.bmp] [--quiet]
 #include <chrono>
+#include <climits>
+#include <cstdint>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -106,11 +108,17 @@ static bool update() {  // skeleton.cpp:282-361, deterministic part
 }
 
 static void append_scene(const char *path_or_null) {
-  int n = path_or_null ? -uob_load_obj(path_or_null, nullptr, nullptr, nullptr, 0) : uob_test_model_count();
-  if (path_or_null && n < 0) n = -n;
-  if (path_or_null && uob_load_obj(path_or_null, nullptr, nullptr, nullptr, 0) == INT32_MIN) {
-    fprintf(stderr, "Error: could not read OBJ file: %s\n", path_or_null);
-    exit(EXIT_FAILURE);
+  int n;
+  if (path_or_null) {
+    // one counting call (capacity 0): INT32_MIN = unreadable file or bad face index, otherwise minus the triangle count
+    const int rc = uob_load_obj(path_or_null, nullptr, nullptr, nullptr, 0);
+    if (rc == INT32_MIN) {
+      fprintf(stderr, "Error: could not read OBJ file: %s\n", path_or_null);
+      exit(EXIT_FAILURE);
+    }
+    n = rc < 0 ? -rc : rc;
+  } else {
+    n = uob_test_model_count();
   }
   const size_t old = (size_t)triangles.n;
   triangles.verts.resize(12 * (old + n));

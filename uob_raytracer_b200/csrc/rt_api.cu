@@ -129,158 +129,63 @@ static void visible_rect_of(const float scene_lo[3], const float scene_hi[3], Fr
   fp.vis_y1 = (int)fmax(0.0, fmin((double)fp.H, hi_y));
 }
 
-// Can a primary ray of the 16x16 tile at (tile_x, tile_y) reach one of the two spheres?  Host-side version of the cone
-// test in the kernel prologue, a little wider; it only chooses the lane mapping of the tile.
-static bool tile_may_see_sphere(const FrameParams &fp, int tile_x, int tile_y) {
-  const float A = (float)fp.A;
-  const float vx0 = (float)(tile_x * fp.A) - (float)fp.W * A * 0.5f, vy0 = (float)(tile_y * fp.A) - (float)fp.H * A * 0.5f;
-  const float vx1 = vx0 + (float)(kTileW * fp.A - 1), vy1 = vy0 + (float)(kTileH * fp.A - 1);
-  float dc[4][3], dm[3] = {0, 0, 0};
-  for (int c = 0; c < 4; c++) {
-    const float vx = (c & 1) ? vx1 : vx0, vy = (c & 2) ? vy1 : vy0;
-    for (int r = 0; r < 3; r++) dc[c][r] = fp.rot[3 * r] * vx + fp.rot[3 * r + 1] * vy + fp.rot[3 * r + 2] * fp.focal;
-  }
-  for (int r = 0; r < 3; r++) dm[r] = 0.5f * (dc[0][r] + dc[3][r]);
-  const float lm = sqrtf(dm[0] * dm[0] + dm[1] * dm[1] + dm[2] * dm[2]);
-  float cos_t = 1.0f;
-  for (int c = 0; c < 4; c++) {
-    const float lc = sqrtf(dc[c][0] * dc[c][0] + dc[c][1] * dc[c][1] + dc[c][2] * dc[c][2]);
-    cos_t = fminf(cos_t, (dm[0] * dc[c][0] + dm[1] * dc[c][1] + dm[2] * dc[c][2]) / (lm * lc));
-  }
-  if (!(cos_t > 0.0f)) return true;
-  const float th_t = acosf(fminf(cos_t, 1.0f));
-  for (int i = 0; i < RT_SPHERES; i++) {
-    const float L[3] = {rt::kSphereCenterR2[i][0] - fp.cam[0], rt::kSphereCenterR2[i][1] - fp.cam[1], rt::kSphereCenterR2[i][2] - fp.cam[2]};
-    const float l2 = L[0] * L[0] + L[1] * L[1] + L[2] * L[2], r2 = rt::kSphereCenterR2[i][3];
-    if (l2 <= r2 * 1.001f) return true;
-    const float th_s = asinf(fminf(sqrtf(r2 / l2), 1.0f));
-    const float cosang = (dm[0] * L[0] + dm[1] * L[1] + dm[2] * L[2]) / (lm * sqrtf(l2));
-    if (acosf(fmaxf(fminf(cosang, 1.0f), -1.0f)) <= th_t + th_s + 2e-3f) return true;
-  }
-  return false;
-}
-
-// Launch-order lists of a mixed launch (pure host code, also reached through rt_debug_tile_lists): `both` = the ordinary
-// 16x16 tiles that cannot see a sphere, then the 8x8 sub-tiles of those that can; returns the length of the first part.
-static size_t build_mixed_lists(const FrameParams &fp, std::vector<int> &both) {
+// Mixed launches: the region rendered with four lanes per pixel is the screen rectangle of each sphere, rounded out to
+// whole 16x16 tiles of the launch's grid.  In camera space (w = R^-1 (P - cam); the ray through sub-pixel (vx, vy) is
+// (vx, vy, f)) the silhouette of a sphere with centre c and radius r spans, along x, the slopes x/z = k of the two planes
+// through the camera and the y axis that touch it:  k = (cx cz -+ r sqrt(cx^2 + cz^2 - r^2)) / (cz^2 - r^2)  (likewise y),
+// valid while the sphere lies wholly in front of the camera (cz > r); otherwise the whole launch is one rectangle.
+// The rectangles only steer performance — either lane mapping renders any tile correctly — so nothing here needs to be
+// conservative; two pixels of margin keep the silhouette inside anyway.  Pure arithmetic, redone for every launch: a
+// moving camera costs nothing (no tables, no copies, no synchronisation).
+int sphere_rects(FrameParams &fp) {
   const int gx = (fp.W + kTileW - 1) / kTileW, gy = (fp.rows + kTileH - 1) / kTileH;
-  const int sgx = (fp.W + kSplitTileW - 1) / kSplitTileW;
-  const float cx = 0.5f * (float)fp.W, cy = 0.5f * (float)fp.H;
-  std::vector<std::pair<float, int>> lt, st;
-  // The split sub-tiles start in order of expected cost — distance from the nearest sphere's projected centre, in
-  // units of its projected radius (the bounce chains are longest through the middle of the glass sphere) — so that
-  // the interleave deals the expensive ones evenly over the ranks and none of them is left for the end.
-  double sph[RT_SPHERES][3];
-  int n_sph = 0;
-  {
-    double inv[9];
-    if (inverse_rotation(fp, inv))
-      for (int i = 0; i < RT_SPHERES; i++) {
-        const double P[3] = {(double)rt::kSphereCenterR2[i][0] - fp.cam[0], (double)rt::kSphereCenterR2[i][1] - fp.cam[1],
-                             (double)rt::kSphereCenterR2[i][2] - fp.cam[2]};
-        double px, py, depth;
-        if (!project_point(fp, inv, P, &px, &py, &depth)) continue;
-        sph[n_sph][0] = px;
-        sph[n_sph][1] = py;
-        sph[n_sph][2] = fmax(1.0, sqrt((double)rt::kSphereCenterR2[i][3]) * fp.focal / depth / fp.A);  // radius in pixels
-        n_sph++;
-      }
+  fp.n_rect = 0;
+  fp.rect_first[0] = fp.rect_first[1] = 0;
+  auto whole = [&]() {
+    fp.n_rect = 1;
+    fp.rect[0][0] = 0;
+    fp.rect[0][1] = 0;
+    fp.rect[0][2] = gx;
+    fp.rect[0][3] = gy;
+    return 4 * gx * gy;
+  };
+  double inv[9];
+  if (!inverse_rotation(fp, inv)) return whole();
+  int total = 0;
+  for (int i = 0; i < RT_SPHERES; i++) {
+    const double P[3] = {(double)rt::kSphereCenterR2[i][0] - fp.cam[0], (double)rt::kSphereCenterR2[i][1] - fp.cam[1],
+                         (double)rt::kSphereCenterR2[i][2] - fp.cam[2]};
+    const double cx = inv[0] * P[0] + inv[1] * P[1] + inv[2] * P[2], cy = inv[3] * P[0] + inv[4] * P[1] + inv[5] * P[2],
+                 cz = inv[6] * P[0] + inv[7] * P[1] + inv[8] * P[2];
+    const double r = sqrt((double)rt::kSphereCenterR2[i][3]) * 1.001;
+    if (!(cz > -r)) continue;            // wholly behind the camera: no primary ray sees it
+    if (!(cz > r * 1.001)) return whole();  // the camera plane cuts the sphere (or the camera is inside it)
+    const double den = cz * cz - r * r;
+    const double sx = r * sqrt(cx * cx + den), sy = r * sqrt(cy * cy + den);
+    const double kx0 = (cx * cz - sx) / den, kx1 = (cx * cz + sx) / den, ky0 = (cy * cz - sy) / den, ky1 = (cy * cz + sy) / den;
+    // sub-pixel coordinate v = f k; pixel = (v + W A / 2) / A
+    const double px0 = (fp.focal * kx0 + 0.5 * fp.W * fp.A) / fp.A, px1 = (fp.focal * kx1 + 0.5 * fp.W * fp.A) / fp.A;
+    const double py0 = (fp.focal * ky0 + 0.5 * fp.H * fp.A) / fp.A, py1 = (fp.focal * ky1 + 0.5 * fp.H * fp.A) / fp.A;
+    if (!(fabs(px0) < 1e9 && fabs(px1) < 1e9 && fabs(py0) < 1e9 && fabs(py1) < 1e9)) return whole();
+    const double x0 = fmax(0.0, floor(px0) - 2.0), x1 = fmin((double)fp.W, floor(px1) + 3.0);
+    const double y0 = fmax((double)fp.row0, floor(py0) - 2.0), y1 = fmin((double)(fp.row0 + fp.rows), floor(py1) + 3.0);
+    if (!(x0 < x1 && y0 < y1)) continue;  // outside the frame or this row range
+    int *q = fp.rect[fp.n_rect];
+    q[0] = (int)x0 / kTileW;
+    q[1] = ((int)y0 - fp.row0) / kTileH;
+    q[2] = std::min(gx, ((int)x1 + kTileW - 1) / kTileW);
+    q[3] = std::min(gy, ((int)y1 - fp.row0 + kTileH - 1) / kTileH);
+    fp.rect_first[fp.n_rect] = total;
+    total += 4 * (q[2] - q[0]) * (q[3] - q[1]);
+    fp.n_rect++;
   }
-  for (int by = 0; by < gy; by++)
-    for (int bx = 0; bx < gx; bx++) {
-      const int tx = bx * kTileW, ty = fp.row0 + by * kTileH;
-      if (!tile_may_see_sphere(fp, tx, ty)) {
-        const float x = (float)(tx + kTileW / 2) - cx, y = (float)(ty + kTileH / 2) - cy;
-        lt.emplace_back(x * x + y * y, by * gx + bx);
-        continue;
-      }
-      for (int sy = 0; sy < kTileH / kSplitTileH; sy++)
-        for (int sx = 0; sx < kTileW / kSplitTileW; sx++) {
-          const int px = tx + sx * kSplitTileW, py = ty + sy * kSplitTileH;
-          if (px >= fp.W || py >= fp.row0 + fp.rows) continue;
-          float cost_key = 0.0f;
-          if (n_sph == 0) {
-            const float x = (float)(px + kSplitTileW / 2) - cx, y = (float)(py + kSplitTileH / 2) - cy;
-            cost_key = x * x + y * y;
-          } else {
-            double best = 1e300;
-            for (int i = 0; i < n_sph; i++) {
-              const double dx = (px + kSplitTileW / 2) - sph[i][0], dy = (py + kSplitTileH / 2) - sph[i][1];
-              best = fmin(best, sqrt(dx * dx + dy * dy) / sph[i][2] + (i == 0 ? 0.0 : 0.5));  // sphere 0 is the glass one
-            }
-            cost_key = (float)best;
-          }
-          st.emplace_back(cost_key, (by * (kTileH / kSplitTileH) + sy) * sgx + bx * (kTileW / kSplitTileW) + sx);
-        }
-    }
-  std::sort(lt.begin(), lt.end());
-  std::sort(st.begin(), st.end());
-  both.clear();
-  both.reserve(lt.size() + st.size() + 1);
-  for (const auto &e : lt) both.push_back(e.second);
-  for (const auto &e : st) both.push_back(e.second);
-  shuffle_windows(both, 0, lt.size());
-  shuffle_windows(both, lt.size(), lt.size() + st.size());
-  return lt.size();
+  return total;
 }
 
-bool mixed_tables_for(rt_ctx *ctx, const FrameParams &fp, cudaStream_t stream, const int **light, int *n_light, const int **split,
-                      int *n_split) {
-  float key[16] = {fp.rot[0], fp.rot[1], fp.rot[2], fp.rot[3], fp.rot[4], fp.rot[5], fp.rot[6], fp.rot[7], fp.rot[8],
-                   fp.cam[0], fp.cam[1], fp.cam[2], fp.focal, (float)fp.A, (float)fp.row0, (float)fp.rows};
-  rt_ctx::MixedTables *hit = nullptr, *victim = &ctx->mixed[0];
-  for (auto &e : ctx->mixed) {
-    if (e.valid && memcmp(key, e.key, sizeof key) == 0) hit = &e;
-    if (!e.valid ? victim->valid : (victim->valid && e.last_use < victim->last_use)) victim = &e;
-  }
-  rt_ctx::MixedTables &m = hit ? *hit : *victim;
-  m.last_use = ++ctx->mixed_clock;
-  if (!hit) {
-    std::vector<int> both;
-    const size_t n_light_tiles = build_mixed_lists(fp, both);
-    const size_t n_split_tiles = both.size() - n_light_tiles;
-    both.push_back(0);
-    // a frame in flight (on any stream of this context) may still be reading the tables this slot held
-    if (m.valid && cudaDeviceSynchronize() != cudaSuccess) {
-      cudaGetLastError();
-      m.valid = false;
-      return false;
-    }
-    if (m.capacity < both.size()) {
-      if (m.d_tables) cudaFree(m.d_tables);
-      m.d_tables = nullptr;
-      m.capacity = 0;
-      if (cudaMalloc(&m.d_tables, sizeof(int) * both.size()) != cudaSuccess) {
-        cudaGetLastError();
-        m.valid = false;
-        return false;
-      }
-      m.capacity = both.size();
-    }
-    // pageable source: the copy is staged before the call returns, and it is ordered before the launch on the stream
-    if (cudaMemcpyAsync(m.d_tables, both.data(), sizeof(int) * both.size(), cudaMemcpyHostToDevice, stream) != cudaSuccess ||
-        cudaStreamSynchronize(stream) != cudaSuccess) {
-      cudaGetLastError();
-      m.valid = false;
-      return false;
-    }
-    m.n_light = (int)n_light_tiles;
-    m.n_split = (int)n_split_tiles;
-    memcpy(m.key, key, sizeof key);
-    m.valid = true;
-  }
-  *light = m.d_tables;
-  *n_light = m.n_light;
-  *split = m.d_tables + m.n_light;
-  *n_split = m.n_split;
-  return true;
-}
-
-const int *tile_order_for(rt_ctx *ctx, int row0, int rows, int grid_x, int n_blocks, int tile_w, int tile_h) {
-  for (const auto &t : ctx->tile_orders)
-    if (t.row0 == row0 && t.rows == rows && t.tile_h == tile_h && t.tile_w == tile_w) return t.d_order;
+// centre-out launch order of the tile grid of rows [row0, row0 + rows) (pure host code)
+static std::vector<int> build_tile_order(int W, int H, int row0, int grid_x, int n_blocks, int tile_w, int tile_h) {
   std::vector<std::pair<float, int>> key((size_t)n_blocks);
-  const float cx = 0.5f * (float)ctx->cfg.width, cy = 0.5f * (float)ctx->cfg.height;
+  const float cx = 0.5f * (float)W, cy = 0.5f * (float)H;
   for (int b = 0; b < n_blocks; b++) {
     const int by = b / grid_x, bx = b - by * grid_x;
     const float x = (float)(bx * tile_w + tile_w / 2) - cx, y = (float)(row0 + by * tile_h + tile_h / 2) - cy;
@@ -290,6 +195,13 @@ const int *tile_order_for(rt_ctx *ctx, int row0, int rows, int grid_x, int n_blo
   std::vector<int> order((size_t)n_blocks);
   for (int b = 0; b < n_blocks; b++) order[(size_t)b] = key[(size_t)b].second;
   shuffle_windows(order, 0, order.size());
+  return order;
+}
+
+const int *tile_order_for(rt_ctx *ctx, int row0, int rows, int grid_x, int n_blocks, int tile_w, int tile_h) {
+  for (const auto &t : ctx->tile_orders)
+    if (t.row0 == row0 && t.rows == rows && t.tile_h == tile_h && t.tile_w == tile_w) return t.d_order;
+  const std::vector<int> order = build_tile_order(ctx->cfg.width, ctx->cfg.height, row0, grid_x, n_blocks, tile_w, tile_h);
   int *d = nullptr;
   if (cudaMalloc(&d, sizeof(int) * (size_t)(n_blocks ? n_blocks : 1)) != cudaSuccess) {
     cudaGetLastError();
@@ -299,6 +211,12 @@ const int *tile_order_for(rt_ctx *ctx, int row0, int rows, int grid_x, int n_blo
     cudaGetLastError();
     cudaFree(d);
     return nullptr;
+  }
+  if (ctx->tile_orders.size() >= 64) {
+    // a caller cycling through many row ranges: drop the old tables once nothing in flight can still read them
+    cudaDeviceSynchronize();
+    for (auto &t : ctx->tile_orders) cudaFree(t.d_order);
+    ctx->tile_orders.clear();
   }
   ctx->tile_orders.push_back(rt_ctx::TileOrder{row0, rows, tile_w, tile_h, d});
   return d;
@@ -352,8 +270,6 @@ static int free_ctx(rt_ctx *ctx) {
     if (ctx->slot_copy_done[sl]) cudaEventDestroy(ctx->slot_copy_done[sl]);
   }
   if (ctx->d_frame_alt) cudaFree(ctx->d_frame_alt);
-  for (auto &e : ctx->mixed)
-    if (e.d_tables) cudaFree(e.d_tables);
   if (ctx->ev0) cudaEventDestroy(ctx->ev0);
   if (ctx->ev1) cudaEventDestroy(ctx->ev1);
   if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
@@ -411,6 +327,7 @@ rt_ctx *rt_create(const rt_config *cfg) {
   cudaDeviceProp prop;
   if ((e = cudaGetDeviceProperties(&prop, cfg->device)) != cudaSuccess) return fail("querying device", e);
   ctx->sm_count = prop.multiProcessorCount;
+  ctx->smem_optin = prop.sharedMemPerBlockOptin;
   if ((e = cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking)) != cudaSuccess) return fail("creating stream", e);
   ctx->stream = ctx->own_stream;
   if ((e = cudaEventCreate(&ctx->ev0)) != cudaSuccess) return fail("creating event", e);
@@ -478,8 +395,11 @@ int rt_upload_scene(rt_ctx *ctx, const float *verts, const float *normals, const
   // Shadow casters: everything except material == -1 (kernels.cl:247)
   int n_sh = 0;
   for (int i = 0; i < n; i++) n_sh += (colors[4 * i + 3] != -1.0f);
-  const size_t smem = rt::brute_smem_bytes(n, n_sh);
-  const bool brute_ok = smem <= rt::brute_smem_limit();
+  // The brute-force path keeps the whole scene in shared memory: the scene arrays, what the fast kernels add per launch
+  // for this context's shadow-sample count (parked hits + jitter columns) and the kernels' static shared memory must fit
+  // the device's opt-in limit per block (227 KB on sm_100) — otherwise the scene goes through the BVH.
+  const size_t smem = rt::brute_smem_bytes(n, n_sh) + rt::fast_extra_smem(ctx->cfg.shadow_samples) + rt::kDrawStaticSmem;
+  const bool brute_ok = smem <= ctx->smem_optin;
   bool use_bvh = !brute_ok;
   if (ctx->cfg.flags & RT_FLAG_FORCE_BVH) use_bvh = true;
   if ((ctx->cfg.flags & RT_FLAG_FORCE_BRUTE) && !brute_ok) {
@@ -655,11 +575,23 @@ int rt_render(rt_ctx *ctx, const float rot12[12], const float cam[4], const floa
     const int rows = (r + band_rows <= ctx->rows) ? band_rows : ctx->rows - r;
     RT_CUDA(ctx, cudaStreamWaitEvent(bs, ctx->band_start, 0), "ordering a band after the stream");
     int rc = render_impl(ctx, rot12, cam, light, focal, nullptr, bs, ctx->row0 + r, rows);
-    if (rc != RT_OK) return rc;
-    const size_t off = (size_t)(ctx->row0 + r) * W;
-    RT_CUDA(ctx, cudaMemcpyAsync(host_argb + (size_t)r * W, ctx->d_frame + off, sizeof(uint32_t) * (size_t)rows * W, cudaMemcpyDeviceToHost, bs),
-            "reading screen buffer data");
-    RT_CUDA(ctx, cudaEventRecord(ctx->band_done[nb], bs), "recording band completion");
+    if (rc == RT_OK) {
+      const size_t off = (size_t)(ctx->row0 + r) * W;
+      cudaError_t e = cudaMemcpyAsync(host_argb + (size_t)r * W, ctx->d_frame + off, sizeof(uint32_t) * (size_t)rows * W, cudaMemcpyDeviceToHost, bs);
+      if (e == cudaSuccess) e = cudaEventRecord(ctx->band_done[nb], bs);
+      if (e != cudaSuccess) {
+        ctx->err = std::string("CUDA error during 'reading screen buffer data': ") + cudaGetErrorString(e);
+        rc = RT_ERR_CUDA;
+      }
+    }
+    if (rc != RT_OK) {
+      // leave nothing in flight that still writes into the caller's buffer: join the bands already started
+      const std::string why = ctx->err;
+      for (int b = 0; b <= nb && b < rt_ctx::kBands; b++) cudaStreamSynchronize(ctx->band_stream[b]);
+      cudaGetLastError();
+      ctx->err = why;
+      return rc;
+    }
   }
   for (int b = 0; b < nb; b++) RT_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->band_done[b], 0), "joining the bands");
   RT_CUDA(ctx, cudaEventRecord(ctx->ev1, ctx->stream), "recording stop event");
@@ -878,12 +810,30 @@ int rt_debug_tile_lists(const rt_config *cfg, const float rot12[12], const float
   if (!cfg || !rot12 || !cam || !n_light || !n_split || capacity < 0 || (capacity > 0 && !tiles)) return RT_ERR_INVALID;
   rt::FrameParams fp;
   debug_frame_params(cfg, rot12, cam, focal, fp);
-  std::vector<int> both;
-  const size_t nl = rt::build_mixed_lists(fp, both);
-  *n_light = (int)nl;
-  *n_split = (int)(both.size() - nl);
-  if ((size_t)capacity < both.size()) return RT_ERR_INVALID;
-  for (size_t i = 0; i < both.size(); i++) tiles[i] = both[i];
+  // what a mixed launch over these rows renders, block by block (rt_launch.cuh: tile_of_block)
+  const int gx = (fp.W + rt::kTileW - 1) / rt::kTileW, gy = (fp.rows + rt::kTileH - 1) / rt::kTileH, sgx = (fp.W + rt::kSplitTileW - 1) / rt::kSplitTileW;
+  const int n_sub = rt::sphere_rects(fp);
+  auto in_rect = [&](int r, int bx, int by) { return bx >= fp.rect[r][0] && bx < fp.rect[r][2] && by >= fp.rect[r][1] && by < fp.rect[r][3]; };
+  std::vector<int> light, split;
+  for (int t : rt::build_tile_order(fp.W, fp.H, fp.row0, gx, gx * gy, rt::kTileW, rt::kTileH)) {
+    const int by = t / gx, bx = t - by * gx;
+    bool split_it = false;
+    for (int r = 0; r < fp.n_rect; r++) split_it |= in_rect(r, bx, by);
+    if (!split_it) light.push_back(t);
+  }
+  for (int gb = 0; gb < n_sub; gb++) {
+    const int r = (fp.n_rect > 1 && gb >= fp.rect_first[1]) ? 1 : 0;
+    const int local = gb - fp.rect_first[r], sw = 2 * (fp.rect[r][2] - fp.rect[r][0]);
+    const int sy = local / sw, sx = local - sy * sw, bx = 2 * fp.rect[r][0] + sx, by = 2 * fp.rect[r][1] + sy;
+    if (r == 1 && in_rect(0, bx >> 1, by >> 1)) continue;
+    if (bx * rt::kSplitTileW >= fp.W || by * rt::kSplitTileH >= fp.rows) continue;  // the block finds no pixel of the frame and exits
+    split.push_back(by * sgx + bx);
+  }
+  *n_light = (int)light.size();
+  *n_split = (int)split.size();
+  if ((size_t)capacity < light.size() + split.size()) return RT_ERR_INVALID;
+  std::copy(light.begin(), light.end(), tiles);
+  std::copy(split.begin(), split.end(), tiles + light.size());
   return RT_OK;
 }
 
@@ -907,5 +857,7 @@ float rt_last_kernel_ms(rt_ctx *ctx) {
 uint64_t rt_kernel_launches(const rt_ctx *ctx) { return ctx ? ctx->launches : 0; }
 
 const char *rt_scene_mode(const rt_ctx *ctx) { return (ctx && ctx->use_bvh) ? "bvh" : "brute"; }
+
+const char *rt_last_kernel_name(const rt_ctx *ctx) { return ctx ? ctx->last_kernel.c_str() : ""; }
 
 }  // extern "C"

@@ -4,6 +4,8 @@
 
 #include <vector>
 
+#include <stdio.h>
+
 #include "rt_bvh.cuh"
 #include "rt_launch.cuh"
 
@@ -255,7 +257,12 @@ static cudaError_t launch_bvh_t(rt_ctx *ctx, const FrameParams &fp_in, cudaStrea
   fp.blk_stride = ctx->cfg.block_stride > 1 ? ctx->cfg.block_stride : 1;
   fp.blk_phase = ctx->cfg.block_stride > 1 ? ctx->cfg.block_phase : 0;
   fp.tile_order = tile_order_for(ctx, fp.row0, fp.rows, fp.grid_x, fp.n_blocks, kTileW, kTileH);
+  fp.n_split = 0;
+  fp.n_rect = 0;
   const int my_blocks = (fp.n_blocks - fp.blk_phase + fp.blk_stride - 1) / fp.blk_stride;
+  char name[64];
+  snprintf(name, sizeof name, "draw_bvh_kernel<%s,%d>", is_strict<T>::value ? "sfloat" : "float", CH);
+  ctx->last_kernel = name;
   if (my_blocks <= 0) return cudaSuccess;
   draw_bvh_kernel<T, CH><<<my_blocks, kThreads, 0, stream>>>(fp, *static_cast<const BvhView *>(ctx->bvh_view));
   ctx->launches++;

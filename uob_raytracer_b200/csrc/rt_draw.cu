@@ -27,7 +27,11 @@ __global__ void __launch_bounds__(kThreads) draw_brute_kernel(const __grid_const
 // strict kernel: 5n + 3n_sh float4; fast kernel: 5n (generic) + 3n (primary constants) + 5n_sh
 // (shadow records) float4 + n ints (binned triangle list) + n_sh ints (identity caster list)
 size_t brute_smem_bytes(int n, int n_sh) { return sizeof(float4) * (size_t)scene_smem_float4(n, n_sh); }
-size_t brute_smem_limit() { return 200 * 1024; }
+// what launch_fast_ch<CH> adds for the chunk size RT_DISPATCH_CH picks for S shadow samples
+size_t fast_extra_smem(int S) {
+  const int ch = S % 10 == 0 ? 10 : S % 8 == 0 ? 8 : S % 5 == 0 ? 5 : S % 4 == 0 ? 4 : S % 2 == 0 ? 2 : 1;
+  return sizeof(float) * (size_t)(3 * ch + 4 * 7) * kThreads;
+}
 
 // Shadow samples are processed CH at a time (fully unrolled): the largest chunk that divides S, so
 // that no padding samples are traced.  The fast kernels are compiled one translation unit per CH
@@ -46,11 +50,11 @@ size_t brute_smem_limit() { return 200 * 1024; }
 cudaError_t launch_draw_brute(rt_ctx *ctx, const FrameParams &fp, cudaStream_t stream) {
   // strict: the culled kernel computes the same frame; RT_FLAG_REFERENCE_LOOPS keeps the plain loop structure
   if ((ctx->cfg.flags & RT_FLAG_STRICT_IEEE) && ((ctx->cfg.flags & RT_FLAG_REFERENCE_LOOPS) || fp.ray_counters)) {
-#define RT_STRICT(CH) launch_kernel(draw_brute_kernel<sfloat, CH>, ctx, fp, stream)
+#define RT_STRICT(CH) launch_kernel(draw_brute_kernel<sfloat, CH>, ctx, fp, stream, 0, "draw_brute_kernel<sfloat," #CH ">")
     RT_DISPATCH_CH(RT_STRICT);
   }
   if (fp.ray_counters) {  // RT_FLAG_COUNT_RAYS: the generic kernel carries the counters
-#define RT_COUNTING(CH) launch_kernel(draw_brute_kernel<float, CH>, ctx, fp, stream)
+#define RT_COUNTING(CH) launch_kernel(draw_brute_kernel<float, CH>, ctx, fp, stream, 0, "draw_brute_kernel<float," #CH ">")
     RT_DISPATCH_CH(RT_COUNTING);
   }
 #define RT_FAST(CH) launch_fast_ch##CH(ctx, fp, stream)

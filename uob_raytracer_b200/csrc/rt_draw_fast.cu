@@ -17,8 +17,7 @@ namespace rt {
 // with its slowest pixel, a glass-sphere pixel whose A*A rays x several bounces form one serial chain — split four
 // ways.  Per-ray contributions are parked and summed in the reference's ray order, so STRICT stays bit-identical.
 template <int CH, bool SINGLE, bool STRICT, bool SPLIT>
-__device__ __forceinline__ void draw_fast_body(const FrameParams &p, const float4 *__restrict__ scene, int n, int n_sh, int block,
-                                               const int *order, int grid_x) {
+__device__ __forceinline__ void draw_fast_body(const FrameParams &p, const float4 *__restrict__ scene, int n, int n_sh, int bx, int by) {
   extern __shared__ float4 smem[];
   __shared__ int s_warp_count[kThreads / 32];
   __shared__ int s_base;
@@ -50,7 +49,7 @@ __device__ __forceinline__ void draw_fast_body(const FrameParams &p, const float
     __syncthreads();
   }
   int x, y, tile_x, tile_y;
-  const bool in_frame = pixel_of_thread<SPLIT>(p, block, order, grid_x, x, y, tile_x, tile_y);
+  const bool in_frame = pixel_of_thread<SPLIT>(p, bx, by, x, y, tile_x, tile_y);
   constexpr int kTW = SPLIT ? kSplitTileW : kTileW, kTH = SPLIT ? kSplitTileH : kTileH;
   if (tile_x >= p.vis_x1 || tile_x + kTW <= p.vis_x0 || tile_y >= p.vis_y1 || tile_y + kTH <= p.vis_y0) {
     // the tile lies outside the projection of the scene's bounding box (at 16:9 the bands beside the Cornell box,
@@ -378,12 +377,15 @@ __device__ __forceinline__ void draw_fast_body(const FrameParams &p, const float
             have_jit = true;
           }
           const float fl = gain * (RT_INDIRECT + direct_light_fast<CH, SINGLE, JittersShared<CH, kThreads>>(sc, hit.point, hit.normal, light, S, global_id, jit));
+          // product and sum rounded separately: the split mapping parks the product and adds it later, and every
+          // lane mapping (hence every multi-GPU partition) has to produce the same bits
+          const V3<float> contrib(__fmul_rn(hit.color.x, fl), __fmul_rn(hit.color.y, fl), __fmul_rn(hit.color.z, fl));
           if constexpr (SPLIT) {
-            q[1 * kThreads] = hit.color.x * fl;
-            q[2 * kThreads] = hit.color.y * fl;
-            q[3 * kThreads] = hit.color.z * fl;
+            q[1 * kThreads] = contrib.x;
+            q[2 * kThreads] = contrib.y;
+            q[3 * kThreads] = contrib.z;
           } else {
-            total = V3<float>(total.x + hit.color.x * fl, total.y + hit.color.y * fl, total.z + hit.color.z * fl);
+            total = V3<float>(__fadd_rn(total.x, contrib.x), __fadd_rn(total.y, contrib.y), __fadd_rn(total.z, contrib.z));
           }
           break;
         }
@@ -412,7 +414,7 @@ __device__ __forceinline__ void draw_fast_body(const FrameParams &p, const float
         const float *c = rec + qq + j * kRec * kThreads;
         const V3<float> v(c[1 * kThreads], c[2 * kThreads], c[3 * kThreads]);
         if constexpr (STRICT) total_s = total_s + V3<SF>(SF(v.x), SF(v.y), SF(v.z));
-        else total = V3<float>(total.x + v.x, total.y + v.y, total.z + v.z);
+        else total = V3<float>(__fadd_rn(total.x, v.x), __fadd_rn(total.y, v.y), __fadd_rn(total.z, v.z));
       }
   }
   if constexpr (STRICT) {
@@ -427,50 +429,59 @@ __device__ __forceinline__ void draw_fast_body(const FrameParams &p, const float
 template <int CH, bool SINGLE, bool STRICT, bool SPLIT>
 __global__ void __launch_bounds__(kThreads, STRICT ? RT_STRICT_MINBLOCKS : RT_MINBLOCKS) draw_fast_kernel(const __grid_constant__ FrameParams p,
                                                                            const float4 *__restrict__ scene, int n, int n_sh) {
-  draw_fast_body<CH, SINGLE, STRICT, SPLIT>(p, scene, n, n_sh, (int)blockIdx.x, p.tile_order, p.grid_x);
+  int bx, by;
+  tile_of_block<SPLIT, false>(p, (int)blockIdx.x, bx, by);
+  draw_fast_body<CH, SINGLE, STRICT, SPLIT>(p, scene, n, n_sh, bx, by);
 }
 
-// Mixed launch for shares of a frame that cannot fill the GPU: tiles that can see a sphere (mirror / glass bounce chains,
-// the pixels a small launch ends up waiting for) are rendered as four 8x8 sub-tiles with four lanes per pixel, by the
-// first n_split blocks of the grid; every other tile by an ordinary block.  The host classifies the tiles per camera
-// (rt_api.cu: mixed_tables_for); the classification only steers performance — either mapping renders any tile correctly.
+// Mixed launch for shares of a frame that cannot fill the GPU: tiles inside the screen rectangle of a sphere (mirror / glass
+// bounce chains, the pixels a small launch ends up waiting for) are rendered as four 8x8 sub-tiles with four lanes per pixel,
+// by the first n_split blocks of the grid; every other tile by an ordinary block.  The rectangles come with the launch
+// arguments (rt_api.cu: sphere_rects) — nothing is built, cached or copied per camera; they only steer performance: either
+// mapping renders any tile correctly.
 template <int CH, bool SINGLE, bool STRICT>
 __global__ void __launch_bounds__(kThreads, STRICT ? RT_STRICT_MINBLOCKS : RT_MINBLOCKS) draw_fast_mixed_kernel(const __grid_constant__ FrameParams p,
                                                                                  const float4 *__restrict__ scene, int n, int n_sh) {
-  if ((int)blockIdx.x < p.n_split)
-    draw_fast_body<CH, SINGLE, STRICT, true>(p, scene, n, n_sh, (int)blockIdx.x, p.split_order, p.split_grid_x);
-  else
-    draw_fast_body<CH, SINGLE, STRICT, false>(p, scene, n, n_sh, (int)blockIdx.x - p.n_split, p.tile_order, p.grid_x);
+  int bx, by;
+  if ((int)blockIdx.x < p.n_split) {
+    if (!tile_of_block<true, true>(p, (int)blockIdx.x, bx, by)) return;
+    draw_fast_body<CH, SINGLE, STRICT, true>(p, scene, n, n_sh, bx, by);
+  } else {
+    if (!tile_of_block<false, true>(p, (int)blockIdx.x - p.n_split, bx, by)) return;
+    draw_fast_body<CH, SINGLE, STRICT, false>(p, scene, n, n_sh, bx, by);
+  }
 }
 
 #define RT_CAT2(a, b) a##b
 #define RT_CAT(a, b) RT_CAT2(a, b)
 
-cudaError_t RT_CAT(launch_fast_ch, RT_FAST_CH)(rt_ctx *ctx, const FrameParams &fp, cudaStream_t stream) {
+cudaError_t RT_CAT(launch_fast_ch, RT_FAST_CH)(rt_ctx *ctx, const FrameParams &fp_in, cudaStream_t stream) {
   constexpr int CH = RT_FAST_CH;
-  ctx->launch_extra_smem = sizeof(float) * (3 * CH + 4 * 7) * kThreads;  // jitter columns + parked primary hits
-  const bool strict = (ctx->cfg.flags & RT_FLAG_STRICT_IEEE) != 0, single = fp.S == CH;
-  const SplitMode mode = split_mode(ctx, fp);
+  const size_t extra = sizeof(float) * (3 * CH + 4 * 7) * kThreads;  // jitter columns + parked primary hits (== fast_extra_smem(S))
+  const bool strict = (ctx->cfg.flags & RT_FLAG_STRICT_IEEE) != 0, single = fp_in.S == CH;
+  FrameParams fp = fp_in;
+  SplitMode mode = split_mode(ctx, fp);
+  int n_sub = 0;
+  if (mode == kSplitHeavy && (n_sub = sphere_rects(fp)) == 0) mode = kSplitNone;  // no sphere in sight: nothing to split
+  char name[96];
+  snprintf(name, sizeof name, "%s<%d,%s,%s%s>", mode == kSplitHeavy ? "draw_fast_mixed_kernel" : "draw_fast_kernel", CH, single ? "true" : "false",
+           strict ? "true" : "false", mode == kSplitHeavy ? "" : (mode == kSplitAll ? ",true" : ",false"));
   if (mode == kSplitHeavy) {
-    const int *light = nullptr, *split = nullptr;
-    int n_light = 0, n_split = 0;
-    if (mixed_tables_for(ctx, fp, stream, &light, &n_light, &split, &n_split)) {
-      if (strict) return single ? launch_kernel_mixed(draw_fast_mixed_kernel<CH, true, true>, ctx, fp, stream, light, n_light, split, n_split)
-                                : launch_kernel_mixed(draw_fast_mixed_kernel<CH, false, true>, ctx, fp, stream, light, n_light, split, n_split);
-      return single ? launch_kernel_mixed(draw_fast_mixed_kernel<CH, true, false>, ctx, fp, stream, light, n_light, split, n_split)
-                    : launch_kernel_mixed(draw_fast_mixed_kernel<CH, false, false>, ctx, fp, stream, light, n_light, split, n_split);
-    }
+    if (strict) return single ? launch_kernel_mixed(draw_fast_mixed_kernel<CH, true, true>, ctx, fp, stream, n_sub, extra, name)
+                              : launch_kernel_mixed(draw_fast_mixed_kernel<CH, false, true>, ctx, fp, stream, n_sub, extra, name);
+    return single ? launch_kernel_mixed(draw_fast_mixed_kernel<CH, true, false>, ctx, fp, stream, n_sub, extra, name)
+                  : launch_kernel_mixed(draw_fast_mixed_kernel<CH, false, false>, ctx, fp, stream, n_sub, extra, name);
   }
   if (mode == kSplitAll) {
-    if (strict) return single ? launch_kernel(draw_fast_kernel<CH, true, true, true>, ctx, fp, stream, kSplitTileW, kSplitTileH)
-                              : launch_kernel(draw_fast_kernel<CH, false, true, true>, ctx, fp, stream, kSplitTileW, kSplitTileH);
-    return single ? launch_kernel(draw_fast_kernel<CH, true, false, true>, ctx, fp, stream, kSplitTileW, kSplitTileH)
-                  : launch_kernel(draw_fast_kernel<CH, false, false, true>, ctx, fp, stream, kSplitTileW, kSplitTileH);
+    if (strict) return single ? launch_kernel(draw_fast_kernel<CH, true, true, true>, ctx, fp, stream, extra, name, kSplitTileW, kSplitTileH)
+                              : launch_kernel(draw_fast_kernel<CH, false, true, true>, ctx, fp, stream, extra, name, kSplitTileW, kSplitTileH);
+    return single ? launch_kernel(draw_fast_kernel<CH, true, false, true>, ctx, fp, stream, extra, name, kSplitTileW, kSplitTileH)
+                  : launch_kernel(draw_fast_kernel<CH, false, false, true>, ctx, fp, stream, extra, name, kSplitTileW, kSplitTileH);
   }
-  if (strict) return single ? launch_kernel(draw_fast_kernel<CH, true, true, false>, ctx, fp, stream)
-                            : launch_kernel(draw_fast_kernel<CH, false, true, false>, ctx, fp, stream);
-  return single ? launch_kernel(draw_fast_kernel<CH, true, false, false>, ctx, fp, stream)
-                : launch_kernel(draw_fast_kernel<CH, false, false, false>, ctx, fp, stream);
+  if (strict) return single ? launch_kernel(draw_fast_kernel<CH, true, true, false>, ctx, fp, stream, extra, name)
+                            : launch_kernel(draw_fast_kernel<CH, false, true, false>, ctx, fp, stream, extra, name);
+  return single ? launch_kernel(draw_fast_kernel<CH, true, false, false>, ctx, fp, stream, extra, name)
+                : launch_kernel(draw_fast_kernel<CH, false, false, false>, ctx, fp, stream, extra, name);
 }
 
 }  // namespace rt

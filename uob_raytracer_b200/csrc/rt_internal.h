@@ -52,24 +52,12 @@ struct rt_ctx {
   uint32_t *d_gate_seen = nullptr;
   int *d_wait_status = nullptr;                  // set by a rt_peer_wait kernel that timed out
   bool peer_waits = false;
-  size_t launch_extra_smem = 0;
+  std::string last_kernel;                      // name of the draw kernel instantiation launched last (rt_last_kernel_name)
+  size_t smem_optin = 0;                        // cudaDevAttrMaxSharedMemoryPerBlockOptin of the device
   // launch-order tables keyed by (row0, rows): centre-out order of the 16-row block grid
   struct TileOrder { int row0, rows, tile_w, tile_h; int *d_order; };
   std::vector<TileOrder> tile_orders;  // set by a launcher that needs shared memory beyond the scene
-  // launch-order tables of mixed launches (ordinary tiles | split sub-tiles), one entry per (camera, row range):
-  // the row bands of rt_render run concurrently on their own streams, each with its own tables
-  struct MixedTables {
-    bool valid = false;
-    float key[16];
-    int *d_tables = nullptr;
-    size_t capacity = 0;
-    int n_light = 0, n_split = 0;
-    unsigned long long last_use = 0;
-  };
   float scene_lo[3] = {0, 0, 0}, scene_hi[3] = {0, 0, 0};  // bounding box of the triangles and the two spheres
-  static constexpr int kMixedSlots = 16;
-  MixedTables mixed[kMixedSlots];
-  unsigned long long mixed_clock = 0;
   std::string err;
 };
 
@@ -78,7 +66,10 @@ namespace rt {
 // rt_draw.cu
 cudaError_t launch_draw_brute(rt_ctx *ctx, const FrameParams &fp, cudaStream_t stream);
 size_t brute_smem_bytes(int n, int n_sh);
-size_t brute_smem_limit();
+// dynamic shared memory the fast kernels need on top of the scene (parked primary hits + jitter columns) for S shadow samples
+size_t fast_extra_smem(int S);
+// static shared memory of the draw kernels (per-warp caster lists, counters), rounded up
+constexpr size_t kDrawStaticSmem = 4608;
 // rt_peak.cu (small utility kernels)
 cudaError_t launch_peer_signal(uint32_t *flag, uint32_t value, cudaStream_t stream);
 cudaError_t launch_peer_wait(const uint32_t *flags, int n, uint32_t value, int *status, cudaStream_t stream);

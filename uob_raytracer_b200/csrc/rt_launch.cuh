@@ -37,16 +37,40 @@ __device__ __forceinline__ SceneView stage_scene(float4 *smem, const float4 *__r
   return sc;
 }
 
-// Pixel tile of this block (top-left corner) and pixel of this thread; false if outside the frame rows.
-// block = index of this block within its list (blockIdx.x, or blockIdx.x - n_split in a mixed launch); order / grid_x =
-// that list's launch-order table and grid width.
-template <bool SPLIT = false>
-__device__ __forceinline__ bool pixel_of_thread(const FrameParams &p, int block, const int *order, int grid_x, int &x, int &y,
-                                                int &tile_x, int &tile_y) {
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+// Which tile does this block render?  block = index of the block within its list (blockIdx.x, or blockIdx.x - n_split for
+// the ordinary blocks of a mixed launch); the list is dealt over the ranks of a multi-GPU interleave (blk_stride / blk_phase)
+// and, for ordinary blocks, permuted by the launch-order table.  (bx, by) = tile coordinates on the launch's tile grid
+// (16x16 tiles, or 8x8 sub-tiles when SPLIT).  False: nothing to do for this block.
+template <bool SPLIT, bool MIXED>
+__device__ __forceinline__ bool tile_of_block(const FrameParams &p, int block, int &bx, int &by) {
   int gb = block * p.blk_stride + p.blk_phase;
-  if (order) gb = order[gb];
-  const int by = gb / grid_x, bx = gb - by * grid_x;
+  if constexpr (SPLIT && MIXED) {
+    // sub-tiles of the sphere rectangles, row-major inside each rectangle, glass sphere first
+    const int r = (p.n_rect > 1 && gb >= p.rect_first[1]) ? 1 : 0;
+    const int local = gb - p.rect_first[r];
+    const int sw = 2 * (p.rect[r][2] - p.rect[r][0]);
+    const int sy = local / sw, sx = local - sy * sw;
+    bx = 2 * p.rect[r][0] + sx;
+    by = 2 * p.rect[r][1] + sy;
+    if (r == 1 && (bx >> 1) >= p.rect[0][0] && (bx >> 1) < p.rect[0][2] && (by >> 1) >= p.rect[0][1] && (by >> 1) < p.rect[0][3])
+      return false;  // rendered as part of rectangle 0
+    return true;
+  } else {
+    if (p.tile_order) gb = p.tile_order[gb];
+    by = gb / p.grid_x;
+    bx = gb - by * p.grid_x;
+    if constexpr (MIXED) {  // tiles inside a sphere rectangle belong to the split blocks
+      for (int r = 0; r < p.n_rect; r++)
+        if (bx >= p.rect[r][0] && bx < p.rect[r][2] && by >= p.rect[r][1] && by < p.rect[r][3]) return false;
+    }
+    return true;
+  }
+}
+
+// Pixel tile of this block (top-left corner) and pixel of this thread; false if outside the frame rows.
+template <bool SPLIT = false>
+__device__ __forceinline__ bool pixel_of_thread(const FrameParams &p, int bx, int by, int &x, int &y, int &tile_x, int &tile_y) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if constexpr (SPLIT) {
     const int pix = lane >> 2;  // 8 pixels per warp, 4 lanes each
     tile_x = bx * kSplitTileW;
@@ -62,9 +86,10 @@ __device__ __forceinline__ bool pixel_of_thread(const FrameParams &p, int block,
   return x < p.W && y < p.row0 + p.rows;
 }
 
-
 __device__ __forceinline__ bool pixel_of_thread(const FrameParams &p, int &x, int &y, int &tile_x, int &tile_y) {
-  return pixel_of_thread<false>(p, (int)blockIdx.x, p.tile_order, p.grid_x, x, y, tile_x, tile_y);
+  int bx, by;
+  tile_of_block<false, false>(p, (int)blockIdx.x, bx, by);
+  return pixel_of_thread<false>(p, bx, by, x, y, tile_x, tile_y);
 }
 
 // rt_api.cu: device table of the launch order for a (row0, rows) range, built on first use
@@ -74,17 +99,17 @@ void visible_rect(const rt_ctx *ctx, FrameParams &fp);
 // rt_api.cu: how should this launch map lanes to pixels? (flags, AA grid, size of the launch)
 enum SplitMode { kSplitNone = 0, kSplitAll = 1, kSplitHeavy = 2 };
 SplitMode split_mode(const rt_ctx *ctx, const FrameParams &fp);
-// rt_api.cu: launch-order tables of a mixed launch for this camera: ordinary 16x16 tiles that cannot see a sphere, and the
-// 8x8 sub-tiles of those that can (both centre-out).  Cached until the camera changes.  False: tables unavailable.
-bool mixed_tables_for(rt_ctx *ctx, const FrameParams &fp, cudaStream_t stream, const int **light, int *n_light, const int **split,
-                      int *n_split);
+// rt_api.cu: the sphere rectangles of a mixed launch for this camera and row range (fills fp.n_rect, fp.rect, fp.rect_first);
+// returns the number of 8x8 sub-tiles they hold.  Pure host arithmetic per launch: nothing is cached, copied or synchronised.
+int sphere_rects(FrameParams &fp);
 
 // float4 slots of the scene part of the fast kernel's shared memory (see brute_smem_bytes)
 __host__ __device__ inline int scene_smem_float4(int n, int n_sh) { return 8 * n + 5 * n_sh + (n + n_sh + 3) / 4 + 1; }
 
+// extra_smem: dynamic shared memory beyond the scene (fast kernels: fast_extra_smem); name: what rt_last_kernel_name reports
 template <class K>
-inline cudaError_t launch_kernel(K kern, rt_ctx *ctx, const FrameParams &fp_in, cudaStream_t stream, int tile_w = kTileW,
-                                 int tile_h = kTileH) {
+inline cudaError_t launch_kernel(K kern, rt_ctx *ctx, const FrameParams &fp_in, cudaStream_t stream, size_t extra_smem, const char *name,
+                                 int tile_w = kTileW, int tile_h = kTileH) {
   FrameParams fp = fp_in;
   fp.grid_x = (fp.W + tile_w - 1) / tile_w;
   fp.n_blocks = fp.grid_x * ((fp.rows + tile_h - 1) / tile_h);
@@ -92,15 +117,14 @@ inline cudaError_t launch_kernel(K kern, rt_ctx *ctx, const FrameParams &fp_in, 
   fp.blk_phase = ctx->cfg.block_stride > 1 ? ctx->cfg.block_phase : 0;
   fp.tile_order = tile_order_for(ctx, fp.row0, fp.rows, fp.grid_x, fp.n_blocks, tile_w, tile_h);
   fp.n_split = 0;
-  fp.split_grid_x = 1;
-  fp.split_order = nullptr;
+  fp.n_rect = 0;
   const int my_blocks = (fp.n_blocks - fp.blk_phase + fp.blk_stride - 1) / fp.blk_stride;
-  const size_t smem = brute_smem_bytes(ctx->n, ctx->n_sh) + ctx->launch_extra_smem;
-  ctx->launch_extra_smem = 0;
-  if (smem > 32 * 1024) {  // dynamic + the kernels' static shared memory (up to 4.2 KB) must stay under the 48 KB default
+  const size_t smem = brute_smem_bytes(ctx->n, ctx->n_sh) + extra_smem;
+  if (smem > 32 * 1024) {  // dynamic + the kernels' static shared memory (kDrawStaticSmem) must stay under the 48 KB default
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
   }
+  ctx->last_kernel = name;
   if (my_blocks <= 0) return cudaSuccess;
   kern<<<my_blocks, kThreads, smem, stream>>>(fp, ctx->d_scene, ctx->n, ctx->n_sh);
   ctx->launches++;
@@ -108,26 +132,25 @@ inline cudaError_t launch_kernel(K kern, rt_ctx *ctx, const FrameParams &fp_in, 
 }
 
 // Mixed launch: this rank's share of the split sub-tiles first (they are the expensive ones), then of the ordinary tiles.
+// fp_in carries the sphere rectangles (sphere_rects); n_sub = sub-tiles they hold.
 template <class K>
-inline cudaError_t launch_kernel_mixed(K kern, rt_ctx *ctx, const FrameParams &fp_in, cudaStream_t stream, const int *light, int n_light,
-                                       const int *split, int n_split) {
+inline cudaError_t launch_kernel_mixed(K kern, rt_ctx *ctx, const FrameParams &fp_in, cudaStream_t stream, int n_sub, size_t extra_smem,
+                                       const char *name) {
   FrameParams fp = fp_in;
   fp.grid_x = (fp.W + kTileW - 1) / kTileW;
-  fp.n_blocks = n_light;
+  fp.n_blocks = fp.grid_x * ((fp.rows + kTileH - 1) / kTileH);
   fp.blk_stride = ctx->cfg.block_stride > 1 ? ctx->cfg.block_stride : 1;
   fp.blk_phase = ctx->cfg.block_stride > 1 ? ctx->cfg.block_phase : 0;
-  fp.tile_order = light;
-  fp.split_order = split;
-  fp.split_grid_x = (fp.W + kSplitTileW - 1) / kSplitTileW;
-  const int my_light = n_light > fp.blk_phase ? (n_light - fp.blk_phase + fp.blk_stride - 1) / fp.blk_stride : 0;
-  const int my_split = n_split > fp.blk_phase ? (n_split - fp.blk_phase + fp.blk_stride - 1) / fp.blk_stride : 0;
+  fp.tile_order = tile_order_for(ctx, fp.row0, fp.rows, fp.grid_x, fp.n_blocks, kTileW, kTileH);
+  const int my_light = fp.n_blocks > fp.blk_phase ? (fp.n_blocks - fp.blk_phase + fp.blk_stride - 1) / fp.blk_stride : 0;
+  const int my_split = n_sub > fp.blk_phase ? (n_sub - fp.blk_phase + fp.blk_stride - 1) / fp.blk_stride : 0;
   fp.n_split = my_split;
-  const size_t smem = brute_smem_bytes(ctx->n, ctx->n_sh) + ctx->launch_extra_smem;
-  ctx->launch_extra_smem = 0;
-  if (smem > 32 * 1024) {  // dynamic + the kernels' static shared memory (up to 4.2 KB) must stay under the 48 KB default
+  const size_t smem = brute_smem_bytes(ctx->n, ctx->n_sh) + extra_smem;
+  if (smem > 32 * 1024) {  // dynamic + the kernels' static shared memory (kDrawStaticSmem) must stay under the 48 KB default
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
   }
+  ctx->last_kernel = name;
   if (my_light + my_split <= 0) return cudaSuccess;
   kern<<<my_light + my_split, kThreads, smem, stream>>>(fp, ctx->d_scene, ctx->n, ctx->n_sh);
   ctx->launches++;

@@ -16,10 +16,14 @@ struct FrameParams {
   // optional launch order: tile_order[k] = row-major block number of the k-th block to start
   // (expensive centre tiles first, so that no long-running block is left for the tail)
   const int *tile_order;
-  // mixed launches (rt_draw_fast.cu): the first n_split blocks of the grid render 8x8-pixel sub-tiles with four lanes
-  // per pixel, taken from split_order (numbered row-major on a grid split_grid_x wide); the rest are ordinary blocks
-  int n_split, split_grid_x;
-  const int *split_order;
+  // mixed launches (rt_draw_fast.cu): the first n_split blocks of the grid render 8x8-pixel sub-tiles with four lanes per
+  // pixel; the rest are ordinary blocks.  The split region is up to two rectangles of 16x16 tiles (the screen rectangles of
+  // the two spheres, rt_api.cu: sphere_rects): rect[r] = {tx0, ty0, tx1, ty1}, half-open, in tiles of this launch's grid
+  // (ty counted from row0).  The sub-tiles of rect r are numbered row-major from rect_first[r]; an ordinary block whose
+  // tile lies in a rectangle exits at once, and so does a sub-tile of rect 1 that rect 0 already covers.
+  int n_split, n_rect;
+  int rect[2][4];
+  int rect_first[2];
   // pixel rectangle [vis_x0, vis_x1) x [vis_y0, vis_y1) outside which no primary ray can hit anything (projection of the
   // scene's bounding box, rt_api.cu): tiles outside it are black without looking at the scene
   int vis_x0, vis_y0, vis_x1, vis_y1;

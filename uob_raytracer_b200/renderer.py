@@ -81,6 +81,11 @@ class Renderer:
     def scene_mode(self) -> str:
         return self._lib.rt_scene_mode(self._ctx).decode()
 
+    @property
+    def last_kernel_name(self) -> str:
+        """The draw kernel instantiation the last render call launched (rt_last_kernel_name)."""
+        return self._lib.rt_last_kernel_name(self._ctx).decode()
+
     # -- rendering -----------------------------------------------------------
     def render(self, rot12, cam, light, focal: float, out: np.ndarray | None = None) -> np.ndarray:
         """Blocking render + read-back of this context's rows. Returns uint32 [rows, width]."""
