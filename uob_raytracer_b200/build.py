@@ -59,14 +59,15 @@ def build(force: bool = False, verbose: bool = False) -> str:
     if not force and not needs_build():
         return LIB
     from concurrent.futures import ThreadPoolExecutor
-    os.makedirs(os.path.join(PKG, "build"), exist_ok=True)
+    objdir = os.environ.get("UOB_BUILD_DIR") or os.path.join(PKG, "build")  # kernel-variant experiments keep their objects apart
+    os.makedirs(objdir, exist_ok=True)
     extra = os.environ.get("UOB_NVCC_DEFS", "").split()
     jobs = [(src, [], src.replace(".cu", ".o")) for src in SOURCES]
     jobs += [("rt_draw_fast.cu", [f"-DRT_FAST_CH={ch}"], f"rt_draw_fast_ch{ch}.o") for ch in FAST_CHUNKS]
 
     def compile_one(job):
         src, defs, obj = job
-        obj = os.path.join(PKG, "build", obj)
+        obj = os.path.join(objdir, obj)
         cmd = [_nvcc(), *NVCC_FLAGS, *extra, *defs, "-c", os.path.join(CSRC, src), "-o", obj]
         if verbose:
             cmd.insert(1, "-Xptxas=-v")
@@ -79,7 +80,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
         logs = list(ex.map(compile_one, jobs))
     if verbose:
         sys.stderr.write("".join(logs))
-    objs = [os.path.join(PKG, "build", j[2]) for j in jobs]
+    objs = [os.path.join(objdir, j[2]) for j in jobs]
     cmd = [_nvcc(), "-Wno-deprecated-gpu-targets", "-shared", "-o", LIB, *objs, "-lcudart"]
     subprocess.check_call(cmd)
     build_skeleton()

@@ -201,7 +201,9 @@ static std::vector<int> build_tile_order(int W, int H, int row0, int grid_x, int
 const int *tile_order_for(rt_ctx *ctx, int row0, int rows, int grid_x, int n_blocks, int tile_w, int tile_h) {
   for (const auto &t : ctx->tile_orders)
     if (t.row0 == row0 && t.rows == rows && t.tile_h == tile_h && t.tile_w == tile_w) return t.d_order;
-  const std::vector<int> order = build_tile_order(ctx->cfg.width, ctx->cfg.height, row0, grid_x, n_blocks, tile_w, tile_h);
+  std::vector<int> order = build_tile_order(ctx->cfg.width, ctx->cfg.height, row0, grid_x, n_blocks, tile_w, tile_h);
+  if (grid_x > 0xffff || (n_blocks + grid_x - 1) / std::max(grid_x, 1) > 0x7fff) return nullptr;  // does not pack: row-major order
+  for (int &t : order) t = ((t / grid_x) << 16) | (t % grid_x);  // what the kernels read: by << 16 | bx
   int *d = nullptr;
   if (cudaMalloc(&d, sizeof(int) * (size_t)(n_blocks ? n_blocks : 1)) != cudaSuccess) {
     cudaGetLastError();
@@ -420,9 +422,9 @@ int rt_upload_scene(rt_ctx *ctx, const float *verts, const float *normals, const
   // Per-triangle constants, computed with the single-rounded operations the
   // reference kernel performs per ray (kernels.cl:102-104 and the cofactors of
   // det, :31-35).  volatile keeps the host compiler from contracting a*b-c*d.
-  std::vector<float4> h(5 * (size_t)n + 8 * (size_t)n_sh);
+  std::vector<float4> h(6 * (size_t)n + 8 * (size_t)n_sh);
   float4 *ta = h.data(), *tb = ta + n, *tc = tb + n, *tn = tc + n, *tcol = tn + n;
-  float4 *sa = tcol + n, *sb = sa + n_sh, *sc = sb + n_sh, *rec = sc + n_sh, *bnd = rec + 4 * (size_t)n_sh;
+  float4 *sa = tcol + n, *sb = sa + n_sh, *sc = sb + n_sh, *rec = sc + n_sh, *bnd = rec + 4 * (size_t)n_sh, *tnd = bnd + n_sh;
   int k = 0;
   for (int i = 0; i < n; i++) {
     const float *v0 = verts + 12 * (size_t)i, *v1 = v0 + 4, *v2 = v0 + 8;
@@ -435,6 +437,9 @@ int rt_upload_scene(rt_ctx *ctx, const float *verts, const float *normals, const
     tc[i] = make_float4(e2x, e2y, e2z, c2);
     tn[i] = make_float4(normals[4 * i], normals[4 * i + 1], normals[4 * i + 2], 0.0f);
     tcol[i] = make_float4(colors[4 * i], colors[4 * i + 1], colors[4 * i + 2], colors[4 * i + 3]);
+    // plane record of the fast policy's bounce rays (rt_fast.cuh: closest_hit_bounce): N = e1 x e2 = (c0, -c1, c2) and
+    // v0.N, so that (o - v0).N = o.N - v0.N and the plane tests of a triangle cost one 16-byte load
+    tnd[i] = make_float4(c0, -c1, c2, v0[0] * c0 - v0[1] * c1 + v0[2] * c2);
     if (colors[4 * i + 3] != -1.0f) {
       sa[k] = ta[i];
       sb[k] = tb[i];

@@ -52,6 +52,7 @@ struct SceneView {
   const float4 *ta, *tb, *tc;  // closest-hit triangles
   const float4 *tn, *tcol;     // normals, colours (w = material)
   const float4 *sa, *sb, *sc;  // shadow casters
+  const float4 *tnd;           // fast kernel only: (N.xyz, v0.N) per triangle, N = e1 x e2 (rt_fast.cuh: closest_hit_bounce)
   int n, n_sh;
 };
 

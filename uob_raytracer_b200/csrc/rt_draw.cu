@@ -24,8 +24,8 @@ __global__ void __launch_bounds__(kThreads) draw_brute_kernel(const __grid_const
   p.out[(size_t)y * p.W + x] = shade_pixel<T, CH, BruteTracer<T>>(tr, p, x, y);
 }
 
-// strict kernel: 5n + 3n_sh float4; fast kernel: 5n (generic) + 3n (primary constants) + 5n_sh
-// (shadow records) float4 + n ints (binned triangle list) + n_sh ints (identity caster list)
+// strict kernel: 5n + 3n_sh float4; fast kernel: 5n (generic) + 3n (primary constants) + 3n (their affine form) + 5n_sh (shadow records and
+// bounds) + n (plane records of the bounce rays) float4 + n ints (binned triangle list) + n_sh ints (identity caster list)
 size_t brute_smem_bytes(int n, int n_sh) { return sizeof(float4) * (size_t)scene_smem_float4(n, n_sh); }
 // what launch_fast_ch<CH> adds for the chunk size RT_DISPATCH_CH picks for S shadow samples
 size_t fast_extra_smem(int S) {

@@ -8,6 +8,12 @@
 
 namespace rt {
 
+#ifdef RT_NO_LAZY  // A/B switch: every primary ray through the reference's exact sequence
+constexpr bool kLazyPrimary = false;
+#else
+constexpr bool kLazyPrimary = true;
+#endif
+
 // CH shadow samples per chunk, SINGLE = (S == CH).  STRICT = RT_FLAG_STRICT_IEEE: same binning, culls and
 // caster lists, but every test that survives them — and all shading arithmetic — runs the reference's exact
 // operation sequence, so the frame is bit-identical to the reference's (and to draw_brute_kernel<sfloat>).
@@ -61,15 +67,17 @@ __device__ __forceinline__ void draw_fast_body(const FrameParams &p, const float
   // ---- stage the scene: generic arrays [0,5n) and the shadow records (global offset 5n+3n_sh) ----
   float4 *const gen = smem;
   float4 *const prim = smem + 5 * n;
-  float4 *const shad = prim + 3 * n;
+  float4 *const aff = prim + 3 * n;
+  float4 *const shad = aff + 3 * n;
   float4 *const sbound = shad + 4 * n_sh;  // bounding sphere of every shadow caster
-  int *const plist = reinterpret_cast<int *>(sbound + n_sh);
+  float4 *const tnd = sbound + n_sh;       // plane record of every triangle (bounce rays of the fast policy)
+  int *const plist = reinterpret_cast<int *>(tnd + n);
   int *const full_list = plist + n;  // 0, 1, ..., n_sh-1: "test every caster"
   // per-thread columns after the lists: parked primary hits (4 x 7 words), then the jitters (SINGLE only)
   float *const rec_base = reinterpret_cast<float *>(smem + scene_smem_float4(n, n_sh));
   float *const jit_base = rec_base + 4 * 7 * kThreads;
   for (int i = threadIdx.x; i < 5 * n; i += kThreads) gen[i] = scene[i];
-  for (int i = threadIdx.x; i < 5 * n_sh; i += kThreads) shad[i] = scene[5 * n + 3 * n_sh + i];  // records + bounding spheres
+  for (int i = threadIdx.x; i < 5 * n_sh + n; i += kThreads) shad[i] = scene[5 * n + 3 * n_sh + i];  // records, bounding spheres, plane records
   for (int i = threadIdx.x; i < n_sh; i += kThreads) full_list[i] = i;
   FastScene sc;
   sc.g.ta = gen;
@@ -78,9 +86,11 @@ __device__ __forceinline__ void draw_fast_body(const FrameParams &p, const float
   sc.g.tn = gen + 3 * n;
   sc.g.tcol = gen + 4 * n;
   sc.g.sa = sc.g.sb = sc.g.sc = nullptr;  // the SoA shadow arrays belong to the generic kernel
+  sc.g.tnd = tnd;
   sc.g.n = n;
   sc.g.n_sh = n_sh;
   sc.prim = prim;
+  sc.aff = aff;
   sc.shad = shad;
   sc.plist = plist;
   const V3<float> cam(p.cam[0], p.cam[1], p.cam[2]), light(p.light[0], p.light[1], p.light[2]);
@@ -138,6 +148,7 @@ __device__ __forceinline__ void draw_fast_body(const FrameParams &p, const float
       bool keep = false;
       if (lane < n) {
         primary_constants(sc.g, prim, cam, lane);
+        if constexpr (!STRICT) primary_affine(prim, aff, lane, p.rot, p.focal, dmax);
         keep = tile_may_hit(prim, lane, dc, dmax);
       }
       const unsigned ballot = __ballot_sync(0xffffffffu, keep);
@@ -149,6 +160,7 @@ __device__ __forceinline__ void draw_fast_body(const FrameParams &p, const float
       bool keep = false;
       if (i < n) {
         primary_constants(sc.g, prim, cam, i);
+        if constexpr (!STRICT) primary_affine(prim, aff, i, p.rot, p.focal, dmax);
         keep = tile_may_hit(prim, i, dc, dmax);
       }
       const unsigned ballot = __ballot_sync(0xffffffffu, keep);
@@ -188,7 +200,7 @@ __device__ __forceinline__ void draw_fast_body(const FrameParams &p, const float
   // SINGLE: the pixel's S jitters, generated on the first shading point (44 % of the 1080p frame
   // lies outside the box and never shades) and kept in shared memory
   JittersShared<CH, kThreads> jit;
-  jit.p = jit_base + threadIdx.x;
+  jit.p = JittersShared<CH, kThreads>::column(jit_base, threadIdx.x);
   bool have_jit = false;
   // Primary ray directions with the reference's operation sequence (kernels.cl:384-405): a handful
   // of operations per ray, and it makes the primary hits bit-identical to the reference.
@@ -226,25 +238,51 @@ __device__ __forceinline__ void draw_fast_body(const FrameParams &p, const float
         ray_dx = 0;
         ray_dy++;
       }
-      const V3<SF> d0 = base + V3<SF>(SF((float)cur_dx), SF((float)cur_dy), SF(0.0f));
-      const V3<SF> dns = normalize(V3<SF>(dot(r0, d0), dot(r1, d0), dot(r2, d0)));
-      int bi;
-      float bt, bu, bv;
-      primary_triangles(sc, V3<float>(dns.x.v, dns.y.v, dns.z.v), bi, bt, bu, bv);
       HitRec<SF> hs;
       hs.id = -1;
       hs.color = make_float4(0.0f, 0.0f, 0.0f, 1.0f);
       hs.point = V3<SF>(SF(0.0f), SF(0.0f), SF(0.0f));
       hs.normal = hs.point;
-      if (bi >= 0) {
-        const V3<SF> v0 = xyz<SF>(sc.g.ta[bi]), e1 = xyz<SF>(sc.g.tb[bi]), e2 = xyz<SF>(sc.g.tc[bi]);
-        hs.id = bi;
-        hs.point = (v0 + scale(SF(bu), e1)) + scale(SF(bv), e2);  // kernels.cl:124
-        hs.normal = xyz<SF>(sc.g.tn[bi]);
-        hs.color = sc.g.tcol[bi];
+      bool exact = true;
+      if constexpr (!STRICT && kLazyPrimary) {
+        // Lazy-exact (rt_fast.cuh: primary_fast): two FMAs per determinant on the sub-pixel coordinates decide every ray
+        // that is not within rounding of a triangle edge, of a tie between two triangles, or of a sphere; no direction,
+        // no normalisation, no division by the reference's rules.  The few rays in doubt take the exact path below.
+        const float vx = base.x.v + (float)cur_dx, vy = base.y.v + (float)cur_dy;  // exact: small integers (or halves)
+        int bi;
+        float bu, bv;
+        exact = !primary_fast(sc, vx, vy, bi, bu, bv);
+        if (!exact && spheres_visible) {
+          const V3<float> w(vx, vy, p.focal);
+          const V3<float> d0(p.rot[0] * w.x + p.rot[1] * w.y + p.rot[2] * w.z, p.rot[3] * w.x + p.rot[4] * w.y + p.rot[5] * w.z,
+                             p.rot[6] * w.x + p.rot[7] * w.y + p.rot[8] * w.z);
+          exact = !spheres_surely_missed(d0, cam);
+        }
+        if (!exact && bi >= 0) {
+          const float4 A0 = sc.g.ta[bi], B0 = sc.g.tb[bi], C0 = sc.g.tc[bi], N0 = sc.g.tn[bi];
+          hs.id = bi;
+          hs.point = V3<SF>(SF(fmaf(bv, C0.x, fmaf(bu, B0.x, A0.x))), SF(fmaf(bv, C0.y, fmaf(bu, B0.y, A0.y))), SF(fmaf(bv, C0.z, fmaf(bu, B0.z, A0.z))));
+          hs.normal = xyz<SF>(N0);
+          hs.color = sc.g.tcol[bi];
+        }
       }
-      // the two spheres, strict as well (skipped when no ray of the block's tile can reach one)
-      if (spheres_visible) closest_spheres<SF>(cam_s, dns, SF(bt), hs);
+      if (exact) {
+        // the reference's own operation sequence (kernels.cl:384-405, :100-163): direction, triangles, spheres
+        const V3<SF> d0 = base + V3<SF>(SF((float)cur_dx), SF((float)cur_dy), SF(0.0f));
+        const V3<SF> dns = normalize(V3<SF>(dot(r0, d0), dot(r1, d0), dot(r2, d0)));
+        int bi;
+        float bt, bu, bv;
+        primary_triangles(sc, V3<float>(dns.x.v, dns.y.v, dns.z.v), bi, bt, bu, bv);
+        if (bi >= 0) {
+          const V3<SF> v0 = xyz<SF>(sc.g.ta[bi]), e1 = xyz<SF>(sc.g.tb[bi]), e2 = xyz<SF>(sc.g.tc[bi]);
+          hs.id = bi;
+          hs.point = (v0 + scale(SF(bu), e1)) + scale(SF(bv), e2);  // kernels.cl:124
+          hs.normal = xyz<SF>(sc.g.tn[bi]);
+          hs.color = sc.g.tcol[bi];
+        }
+        // the two spheres, strict as well (skipped when no ray of the block's tile can reach one)
+        if (spheres_visible) closest_spheres<SF>(cam_s, dns, SF(bt), hs);
+      }
       // sphere i is parked as id -2-i so that phase 3 can recover its colour (kernels.cl:28 uses -2 for both)
       int id = hs.id;
       if (id == -2) id = (hs.color.w == c_sphere_color[0].w) ? -2 : -3;
@@ -330,11 +368,7 @@ __device__ __forceinline__ void draw_fast_body(const FrameParams &p, const float
         while (hs.id != -1) {
           if (hs.color.w > 0.0f) {
             if (SINGLE && !have_jit) {
-              uint32_t rx, ry, rz;
-              seed_rng(global_id, rx, ry, rz);
-              Jitters<CH> jr;
-              make_jitters<CH, true>(rx, ry, rz, jr);
-              jit.store(jr);
+              make_jitters_shared<CH, kThreads, true>(global_id, jit);
               have_jit = true;
             }
             const SF dl = direct_light_strict<CH, SINGLE, JittersShared<CH, kThreads>>(sc, hs.point, hs.normal, light_s, S, global_id, jit);
@@ -369,11 +403,7 @@ __device__ __forceinline__ void draw_fast_body(const FrameParams &p, const float
       while (hit.id != -1) {
         if (hit.color.w > 0.0f) {
           if (SINGLE && !have_jit) {
-            uint32_t rx, ry, rz;
-            seed_rng(global_id, rx, ry, rz);
-            Jitters<CH> jr;
-            make_jitters<CH>(rx, ry, rz, jr);
-            jit.store(jr);
+            make_jitters_shared<CH, kThreads, false>(global_id, jit);
             have_jit = true;
           }
           const float fl = gain * (RT_INDIRECT + direct_light_fast<CH, SINGLE, JittersShared<CH, kThreads>>(sc, hit.point, hit.normal, light, S, global_id, jit));
@@ -397,7 +427,11 @@ __device__ __forceinline__ void draw_fast_body(const FrameParams &p, const float
         dir = ndir;
         hit.id = -1;
         hit.color.w = 1.0f;
+#ifdef RT_NO_BOUNCE_PLANES  // A/B switch: the plain loop over all triangles
         closest_hit<float>(sc.g, start, dir, hit);
+#else
+        closest_hit_bounce(sc.g, start, dir, hit);
+#endif
         gain = 0.9f;
         sc.clist = full_list;  // the warp list was built for the primary hits only
         sc.n_clist = n_sh;

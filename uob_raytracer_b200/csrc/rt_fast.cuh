@@ -55,11 +55,15 @@ namespace rt {
 //   prim[3i+0] = (c0, c1, c2, det[b,e1,e2])     b = cam - v0
 //   prim[3i+1] = (U0, U1, U2, g)                cofactors of det[-d,b,e2] (kernels.cl:31-35 convention)
 //   prim[3i+2] = (V0, V1, V2, 3g)               cofactors of det[-d,e1,b]
+//   aff[3i+0]  = (gA.x, gA.y, f gA.z, det[b,e1,e2])   dn(vx, vy) = vx gA.x + vy gA.y + f gA.z   (see primary_affine)
+//   aff[3i+1]  = (gU.x, gU.y, f gU.z, tau)            E1(vx, vy)
+//   aff[3i+2]  = (gV.x, gV.y, f gV.z, 0)              E2(vx, vy)
 //   shad[4k+0] = (v0.xyz, jmax|N|)   shad[4k+1] = (c0, c1, c2, 0)
 //   shad[4k+2] = (e1.xyz, jmax|e1|)  shad[4k+3] = (e2.xyz, jmax|e2|)     k-th shadow caster
 struct FastScene {
   SceneView g;          // generic SoA arrays (bounce rays, hit attributes)
   const float4 *prim;   // 3 per triangle
+  const float4 *aff;    // 3 per triangle: the same three determinants as affine functions of the sub-pixel coordinates
   const float4 *shad;   // 4 per shadow caster
   const int *plist;     // triangles surviving the block's binning, ascending
   int n_prim;           // entries in plist
@@ -151,6 +155,9 @@ __device__ __forceinline__ void primary_constants(const SceneView &g, float4 *pr
 // filter of primary_triangles.
 __device__ __forceinline__ bool tile_may_hit(const float4 *prim, int i, const V3<float> (&dc)[4], float dmax) {
   const float4 PA = prim[3 * i], PB = prim[3 * i + 1], PC = prim[3 * i + 2];
+  // a triangle without area (cofactors exactly zero): det A = +-0 and det[b,e1,e2] = 0 for every ray, so t = 0/0 is NaN
+  // and every comparison of kernels.cl:120 fails — it is never hit
+  if (PA.x == 0.0f && PA.y == 0.0f && PA.z == 0.0f) return false;
   float dn[4], e1[4], e2[4];
 #pragma unroll
   for (int c = 0; c < 4; c++) {
@@ -173,6 +180,82 @@ __device__ __forceinline__ bool tile_may_hit(const float4 *prim, int i, const V3
     out3 &= (a + b) - fabsf(dn[c]) > 3.0f * tol;
   }
   return !(out1 | out2 | out3);
+}
+
+// The primary ray through sub-pixel (vx, vy) has the un-normalised direction d0 = R (vx, vy, f) (kernels.cl:384-400), and
+// the three determinants of a triangle's test are linear in the direction: dn = d0.a with a = (c0, -c1, c2), hence
+// dn = (vx, vy, f).(R^T a) — an AFFINE function of (vx, vy) whose three coefficients are per-frame constants of the
+// triangle; likewise E1 and E2.  Scaling the direction scales all three alike, so every sign and every ratio (u = E1/dn,
+// v = E2/dn) is that of the reference's normalised ray.  tau bounds the rounding of these evaluations AND of the
+// reference's own strict evaluation: 4e-6 x (largest L1 norm of the cofactor vectors) x (longest d0 of the tile).
+__device__ __forceinline__ void primary_affine(const float4 *prim, float4 *aff, int i, const float *rot, float focal, float dmax) {
+  const float4 PA = prim[3 * i], PB = prim[3 * i + 1], PC = prim[3 * i + 2];
+  auto g = [&](float x, float y, float z, float w) {  // R^T (x, -y, z), third component times f
+    y = -y;
+    return make_float4(rot[0] * x + rot[3] * y + rot[6] * z, rot[1] * x + rot[4] * y + rot[7] * z,
+                       (rot[2] * x + rot[5] * y + rot[8] * z) * focal, w);
+  };
+  aff[3 * i + 0] = g(PA.x, PA.y, PA.z, PA.w);
+  aff[3 * i + 1] = g(PB.x, PB.y, PB.z, PB.w * 2.0f * dmax);
+  aff[3 * i + 2] = g(PC.x, PC.y, PC.z, 0.0f);
+}
+
+// Lazy-exact primary visibility (fast policy).  Classifies every binned triangle for the ray through (vx, vy) as surely
+// missed, surely hit, or too close to call: a margin of tau on every inside test, a relative 1e-5 between the distances
+// of two hits.  True: the decisions are beyond doubt — the reference's strict arithmetic takes the same ones — and
+// best / bu / bv hold the hit (-1 = miss; u, v from approximate division, which only moves the hit point by rounding).
+// False: the caller repeats the ray with the reference's exact sequence (primary_triangles).  The default camera puts
+// box edges exactly on pixel boundaries: those rays are the ones that come back false.
+__device__ __forceinline__ bool primary_fast(const FastScene &sc, float vx, float vy, int &best, float &bu, float &bv) {
+  best = -1;
+  bu = 0.0f;
+  bv = 0.0f;
+  float bt = 0.0f;
+  bool sure = true;
+  for (int l = 0; l < sc.n_prim; l++) {
+    const int i = sc.plist[l];
+    const float4 *q = sc.aff + 3 * i;
+    const float4 QA = q[0], QB = q[1], QC = q[2];
+    const float dn = fmaf(vx, QA.x, fmaf(vy, QA.y, QA.z));
+    const float E1 = fmaf(vx, QB.x, fmaf(vy, QB.y, QB.z));
+    const float E2 = fmaf(vx, QC.x, fmaf(vy, QC.y, QC.z));
+    const unsigned sb = __float_as_uint(dn) & 0x80000000u;
+    const float e1 = xor_sign(E1, sb), e2 = xor_sign(E2, sb), ts = xor_sign(QA.w, sb), adn = fabsf(dn), tau = QB.w;
+    const float slack = adn - (e1 + e2), tau3 = 3.0f * tau;  // (1 - u - v) |dn|
+    const bool dn_ok = adn > tau;                             // the sign of dn is beyond doubt
+    const bool out = (e1 < -tau) | (e2 < -tau) | (slack < -tau3) | (ts > 0.0f);  // u < 0, v < 0, u + v > 1 or t < 0
+    if (dn_ok & out) continue;
+    const bool in = (e1 > tau) & (e2 > tau) & (slack > tau3) & (ts < 0.0f);
+    if (!(dn_ok & in)) {
+      sure = false;
+      continue;
+    }
+    const float inv = rcp_approx(adn);
+    const float t = -ts * inv;  // in units of |d0|: the same scale for every triangle of this ray
+    if (best >= 0 && fabsf(t - bt) <= 1e-5f * (t + bt)) sure = false;  // two hits at (nearly) the same distance: the tie rule decides
+    if (best < 0 || t < bt) {
+      bt = t;
+      best = i;
+      bu = e1 * inv;
+      bv = e2 * inv;
+    }
+  }
+  return sure;
+}
+
+// Does the ray cam + x d0 surely miss both spheres?  (disc/4 = (d0.L)^2 - (d0.d0)(L.L - r^2) < 0 with a relative margin;
+// kernels.cl:132-163.)  Anything else — a hit, a graze, the camera inside a sphere — goes to the exact sequence.
+__device__ __forceinline__ bool spheres_surely_missed(V3<float> d0, V3<float> cam) {
+  bool miss = true;
+  const float a = dot(d0, d0);
+#pragma unroll
+  for (int i = 0; i < RT_SPHERES; i++) {
+    const float4 cr = c_sphere_center_r2[i];
+    const V3<float> L(cam.x - cr.x, cam.y - cr.y, cam.z - cr.z);
+    const float hb = dot(d0, L), h2 = hb * hb, ac = a * (dot(L, L) - cr.w);
+    miss &= (h2 - ac) < -1e-5f * (h2 + fabsf(ac));
+  }
+  return miss;
 }
 
 // Closest triangle for one ray from the camera (kernels.cl:100-129); see the header.
@@ -210,29 +293,76 @@ __device__ __forceinline__ void primary_triangles(const FastScene &sc, V3<float>
   }
 }
 
+// Closest hit of a bounce ray, fast policy (kernels.cl:168-241).  Same decisions as closest_tri_test<float> — the inside
+// test on sign-corrected triple products, t = ts / |dn| compared with strict '<' in ascending index order — behind two
+// plane tests that cost one 16-byte load and six FMAs per triangle:  dn = d.N, bn = (o - v0).N = o.N - v0.N,
+//   t = -bn/dn < 0        (the plane lies behind the ray)              -> skip
+//   |bn| > best_t |dn|    (the plane is crossed beyond the current hit, with a relative margin far above rounding) -> skip
+// A bounce ray inside the box faces about half the planes and, once it has a hit, most of the rest lie behind it; the
+// rays of a warp leave neighbouring points of a sphere, so they mostly agree.  Only survivors load the vertices.
+__device__ __forceinline__ void closest_hit_bounce(const SceneView &sc, V3<float> start, V3<float> dir, HitRec<float> &hit) {
+  ClosestState<float> cs;
+  cs.reset();
+  for (int i = 0; i < sc.n; i++) {
+    const float4 P = sc.tnd[i];
+    const float dn = fmaf(dir.x, P.x, fmaf(dir.y, P.y, dir.z * P.z));
+    const float bn = fmaf(start.x, P.x, fmaf(start.y, P.y, fmaf(start.z, P.z, -P.w)));
+    const unsigned sb = __float_as_uint(dn) & 0x80000000u;
+    const float ts = xor_sign(-bn, sb), adn = fabsf(dn);
+    if (!(ts >= 0.0f) || ts > cs.t * adn * 1.0001f) continue;  // (NaN rays fail the first test, as they fail the full one)
+    const float4 A = sc.ta[i], Bq = sc.tb[i], C = sc.tc[i];
+    const V3<float> b(start.x - A.x, start.y - A.y, start.z - A.z), e1(Bq.x, Bq.y, Bq.z), e2(C.x, C.y, C.z);
+    const V3<float> q(b.y * dir.z - b.z * dir.y, b.z * dir.x - b.x * dir.z, b.x * dir.y - b.y * dir.x);
+    const float us = xor_sign(-dot(e2, q), sb), vs = xor_sign(dot(e1, q), sb);
+    if ((us >= 0.0f) & (vs >= 0.0f) & ((us + vs) <= adn)) {
+      const float inv = __frcp_rn(adn);
+      const float t = ts * inv;
+      if (t < cs.t) {
+        cs.id = i;
+        cs.u = us * inv;
+        cs.v = vs * inv;
+        cs.t = t;
+      }
+    }
+  }
+  if (cs.id >= 0) {
+    hit.id = cs.id;
+    hit.point = hit_point<float>(sc.ta[cs.id], sc.tb[cs.id], sc.tc[cs.id], cs.u, cs.v);
+    hit.normal = xyz<float>(sc.tn[cs.id]);
+    hit.color = sc.tcol[cs.id];
+  }
+  closest_spheres<float>(start, dir, cs.t, hit);
+}
+
 // The S jitters of a pixel: they depend on the pixel id only (kernels.cl:319,331).
 template <int CH> struct Jitters {  // in registers
+  static constexpr bool kPacked = false;
   float x[CH], y[CH], z[CH];
   __device__ __forceinline__ float jx(int k) const { return x[k]; }
   __device__ __forceinline__ float jy(int k) const { return y[k]; }
   __device__ __forceinline__ float jz(int k) const { return z[k]; }
 };
-// The same in shared memory, component-major with a stride of one block so that the threads of a
-// warp read consecutive words: the jitters are only touched once per shading point (|d_k|^2) and by
-// the few (point, triangle) pairs that survive the culls, so they need not occupy 3*CH registers.
+// The same in shared memory, one column per thread with a stride of one block so that the threads of a warp read
+// consecutive words: the jitters are only touched once per shading point (|d_k|^2) and by the few (point, triangle) pairs
+// that survive the culls, so they need not occupy 3*CH registers.  Even CH: samples are stored in PAIRS, component-major —
+// float2 slot (c*CH/2 + k/2)*STRIDE + thread holds (j_c[k], j_c[k+1]) — so one LDS.64 feeds one packed fma.rn.f32x2
+// (two samples per issue slot, rt_fast.cuh: shadow_lit_count).  Odd CH: one float per slot, (3k + c)*STRIDE + thread.
 template <int CH, int STRIDE> struct JittersShared {
-  float *p;  // this thread's column
-  __device__ __forceinline__ float jx(int k) const { return p[(3 * k + 0) * STRIDE]; }
-  __device__ __forceinline__ float jy(int k) const { return p[(3 * k + 1) * STRIDE]; }
-  __device__ __forceinline__ float jz(int k) const { return p[(3 * k + 2) * STRIDE]; }
-  __device__ __forceinline__ void store(const Jitters<CH> &j) const {
-#pragma unroll
-    for (int k = 0; k < CH; k++) {
-      p[(3 * k + 0) * STRIDE] = j.x[k];
-      p[(3 * k + 1) * STRIDE] = j.y[k];
-      p[(3 * k + 2) * STRIDE] = j.z[k];
-    }
-  }
+#ifdef RT_NO_F32X2  // A/B switch: scalar per-sample tests
+  static constexpr bool kPacked = false;
+#else
+  static constexpr bool kPacked = (CH % 2) == 0;
+#endif
+  float *p;  // this thread's column: base + thread (odd CH) or base + 2*thread (even CH)
+  __device__ __forceinline__ static float *column(float *base, int thread) { return base + (kPacked ? 2 * thread : thread); }
+  __device__ __forceinline__ int at(int c, int k) const { return kPacked ? 2 * STRIDE * (c * (CH / 2) + (k >> 1)) + (k & 1) : (3 * k + c) * STRIDE; }
+  __device__ __forceinline__ float jx(int k) const { return p[at(0, k)]; }
+  __device__ __forceinline__ float jy(int k) const { return p[at(1, k)]; }
+  __device__ __forceinline__ float jz(int k) const { return p[at(2, k)]; }
+  // samples 2*k2 and 2*k2 + 1 of one component (kPacked only)
+  __device__ __forceinline__ float2 x2(int k2) const { return *reinterpret_cast<const float2 *>(p + 2 * STRIDE * (0 * (CH / 2) + k2)); }
+  __device__ __forceinline__ float2 y2(int k2) const { return *reinterpret_cast<const float2 *>(p + 2 * STRIDE * (1 * (CH / 2) + k2)); }
+  __device__ __forceinline__ float2 z2(int k2) const { return *reinterpret_cast<const float2 *>(p + 2 * STRIDE * (2 * (CH / 2) + k2)); }
 };
 
 __device__ __forceinline__ void seed_rng(int global_id, uint32_t &rx, uint32_t &ry, uint32_t &rz) {
@@ -255,6 +385,46 @@ __device__ __forceinline__ void make_jitters(uint32_t &rx, uint32_t &ry, uint32_
   }
 }
 
+// The pixel's CH jitters generated straight into its shared-memory column (no register array in between: the compiler
+// parked that one in local memory).  Same sequence as make_jitters.
+template <int CH, int STRIDE, bool STRICT>
+__device__ __forceinline__ void make_jitters_shared(int global_id, const JittersShared<CH, STRIDE> &jit) {
+  typedef typename std::conditional<STRICT, sfloat, float>::type T;
+  uint32_t rx, ry, rz;
+  seed_rng(global_id, rx, ry, rz);
+  if constexpr (JittersShared<CH, STRIDE>::kPacked) {
+#pragma unroll
+    for (int k2 = 0; k2 < CH / 2; k2++) {
+      float2 vx, vy, vz;
+      rx = xorshift32(rx);
+      ry = xorshift32(ry);
+      rz = xorshift32(rz);
+      vx.x = raw(crush1<T>(rx, RT_LIGHT_SPREAD));
+      vy.x = raw(crush1<T>(ry, RT_LIGHT_SPREAD));
+      vz.x = raw(crush1<T>(rz, RT_LIGHT_SPREAD));
+      rx = xorshift32(rx);
+      ry = xorshift32(ry);
+      rz = xorshift32(rz);
+      vx.y = raw(crush1<T>(rx, RT_LIGHT_SPREAD));
+      vy.y = raw(crush1<T>(ry, RT_LIGHT_SPREAD));
+      vz.y = raw(crush1<T>(rz, RT_LIGHT_SPREAD));
+      *reinterpret_cast<float2 *>(jit.p + 2 * STRIDE * (0 * (CH / 2) + k2)) = vx;
+      *reinterpret_cast<float2 *>(jit.p + 2 * STRIDE * (1 * (CH / 2) + k2)) = vy;
+      *reinterpret_cast<float2 *>(jit.p + 2 * STRIDE * (2 * (CH / 2) + k2)) = vz;
+    }
+  } else {
+#pragma unroll
+    for (int k = 0; k < CH; k++) {
+      rx = xorshift32(rx);
+      ry = xorshift32(ry);
+      rz = xorshift32(rz);
+      jit.p[jit.at(0, k)] = raw(crush1<T>(rx, RT_LIGHT_SPREAD));
+      jit.p[jit.at(1, k)] = raw(crush1<T>(ry, RT_LIGHT_SPREAD));
+      jit.p[jit.at(2, k)] = raw(crush1<T>(rz, RT_LIGHT_SPREAD));
+    }
+  }
+}
+
 // Number of UNOCCLUDED samples among the CH shadow rays start + t (r + j_k)  (in_shadow, kernels.cl:243-311).
 // The directions d_k = r + j_k are never materialised: d_k.X = r.X + j_k.X with r.X once per (point, triangle).
 template <int CH, class J>
@@ -262,16 +432,33 @@ __device__ __forceinline__ int shadow_lit_count(const FastScene &sc, V3<float> s
                                                 const J &j, unsigned valid_mask) {
   constexpr unsigned FULL = (CH >= 32) ? 0xffffffffu : ((1u << CH) - 1u);
   unsigned occ = ~valid_mask & FULL;  // padding samples of a ragged chunk count as occluded (ignored by the caller)
-  float dd[CH];                       // |d_k|^2, filled on first use: most points never reach a per-sample test
+  // |d_k|^2, filled on first use: most points never reach a per-sample test.  kPacked: two samples per register pair,
+  // evaluated with the packed FP32 instructions of sm_100 (fma.rn.f32x2: one issue slot, two samples).
+  constexpr bool P = J::kPacked;
+  float dd[P ? 1 : CH];
+  float2 dd2[P ? CH / 2 : 1];
   bool have_dd = false;
   auto need_dd = [&]() {
     if (have_dd) return;
     have_dd = true;
+    if constexpr (P) {
+      const float2 rx2 = make_float2(r.x, r.x), ry2 = make_float2(r.y, r.y), rz2 = make_float2(r.z, r.z);
 #pragma unroll
-    for (int k = 0; k < CH; k++) {
-      const float ddx = r.x + j.jx(k), ddy = r.y + j.jy(k), ddz = r.z + j.jz(k);
-      dd[k] = (ddx * ddx + ddy * ddy) + ddz * ddz;
+      for (int k2 = 0; k2 < CH / 2; k2++) {
+        const float2 ddx = __fadd2_rn(rx2, j.x2(k2)), ddy = __fadd2_rn(ry2, j.y2(k2)), ddz = __fadd2_rn(rz2, j.z2(k2));
+        dd2[k2] = __ffma2_rn(ddz, ddz, __ffma2_rn(ddx, ddx, __fmul2_rn(ddy, ddy)));
+      }
+    } else {
+#pragma unroll
+      for (int k = 0; k < CH; k++) {
+        const float ddx = r.x + j.jx(k), ddy = r.y + j.jy(k), ddz = r.z + j.jz(k);
+        dd[k] = (ddx * ddx + ddy * ddy) + ddz * ddz;
+      }
     }
+  };
+  auto dd_of = [&](int k) -> float {
+    if constexpr (P) return (k & 1) ? dd2[k >> 1].y : dd2[k >> 1].x;
+    else return dd[k];
   };
   // |r| / |d_s| <= R / (R - jmax); no bound (k huge) when the light is closer than 2 jmax
   const float R = sqrt_approx(radius_sq);
@@ -304,19 +491,46 @@ __device__ __forceinline__ int shadow_lit_count(const FastScene &sc, V3<float> s
     const float q1 = num * num * inv_r2;  // t^2 |d|^2 < r^2  <=>  q1 |d|^2 < dn^2
     const unsigned numb = __float_as_uint(num);
     need_dd();
+    // det A = -dn;  t = -num/dn;  u = E1/dn;  v = E2/dn
+    // sign bit of sx clear  <=>  sign(E1) == sign(dn) && sign(E2) == sign(dn) && sign(num) != sign(dn)
+    //                       <=>  u >= 0 && v >= 0 && t >= 0   (exact zeros aside)
+    if constexpr (P) {
+      const float2 c0p = make_float2(c0, c0), c1n = make_float2(-c1, -c1), c2p = make_float2(c2, c2), rNp = make_float2(rN, rN);
+      const float2 Ux = make_float2(U.x, U.x), Uy = make_float2(U.y, U.y), Uz = make_float2(U.z, U.z), rUp = make_float2(rU, rU);
+      const float2 Vx = make_float2(V.x, V.x), Vy = make_float2(V.y, V.y), Vz = make_float2(V.z, V.z), rVp = make_float2(rV, rV);
+      const float2 q1p = make_float2(q1, q1);
 #pragma unroll
-    for (int k = 0; k < CH; k++) {
-      // det A = -dn;  t = -num/dn;  u = E1/dn;  v = E2/dn
-      const float jx = j.jx(k), jy = j.jy(k), jz = j.jz(k);
-      const float dn = fmaf(jx, c0, fmaf(-jy, c1, fmaf(jz, c2, rN)));
-      const float E1 = fmaf(jx, U.x, fmaf(jy, U.y, fmaf(jz, U.z, rU)));
-      const float E2 = fmaf(jx, V.x, fmaf(jy, V.y, fmaf(jz, V.z, rV)));
-      // sign bit of sx clear  <=>  sign(E1) == sign(dn) && sign(E2) == sign(dn) && sign(num) != sign(dn)
-      //                       <=>  u >= 0 && v >= 0 && t >= 0   (exact zeros aside)
-      const unsigned dnb = __float_as_uint(dn);
-      const unsigned sx = ((__float_as_uint(E1) ^ dnb) | (__float_as_uint(E2) ^ dnb)) | ~(numb ^ dnb);
-      const bool hit = ((int)sx >= 0) & (fabsf(E1 + E2) <= fabsf(dn)) & (q1 * dd[k] < dn * dn);
-      occ |= hit ? (1u << k) : 0u;
+      for (int k2 = 0; k2 < CH / 2; k2++) {
+        const float2 jx = j.x2(k2), jy = j.y2(k2), jz = j.z2(k2);
+        const float2 dn = __ffma2_rn(jx, c0p, __ffma2_rn(jy, c1n, __ffma2_rn(jz, c2p, rNp)));
+        const float2 E1 = __ffma2_rn(jx, Ux, __ffma2_rn(jy, Uy, __ffma2_rn(jz, Uz, rUp)));
+        const float2 E2 = __ffma2_rn(jx, Vx, __ffma2_rn(jy, Vy, __ffma2_rn(jz, Vz, rVp)));
+        const float2 es = __fadd2_rn(E1, E2), lhs = __fmul2_rn(q1p, dd2[k2]), rhs = __fmul2_rn(dn, dn);
+        {
+          const unsigned dnb = __float_as_uint(dn.x);
+          const unsigned sx = ((__float_as_uint(E1.x) ^ dnb) | (__float_as_uint(E2.x) ^ dnb)) | ~(numb ^ dnb);
+          const bool hit = ((int)sx >= 0) & (fabsf(es.x) <= fabsf(dn.x)) & (lhs.x < rhs.x);
+          occ |= hit ? (1u << (2 * k2)) : 0u;
+        }
+        {
+          const unsigned dnb = __float_as_uint(dn.y);
+          const unsigned sx = ((__float_as_uint(E1.y) ^ dnb) | (__float_as_uint(E2.y) ^ dnb)) | ~(numb ^ dnb);
+          const bool hit = ((int)sx >= 0) & (fabsf(es.y) <= fabsf(dn.y)) & (lhs.y < rhs.y);
+          occ |= hit ? (2u << (2 * k2)) : 0u;
+        }
+      }
+    } else {
+#pragma unroll
+      for (int k = 0; k < CH; k++) {
+        const float jx = j.jx(k), jy = j.jy(k), jz = j.jz(k);
+        const float dn = fmaf(jx, c0, fmaf(-jy, c1, fmaf(jz, c2, rN)));
+        const float E1 = fmaf(jx, U.x, fmaf(jy, U.y, fmaf(jz, U.z, rU)));
+        const float E2 = fmaf(jx, V.x, fmaf(jy, V.y, fmaf(jz, V.z, rV)));
+        const unsigned dnb = __float_as_uint(dn);
+        const unsigned sx = ((__float_as_uint(E1) ^ dnb) | (__float_as_uint(E2) ^ dnb)) | ~(numb ^ dnb);
+        const bool hit = ((int)sx >= 0) & (fabsf(E1 + E2) <= fabsf(dn)) & (q1 * dd[k] < dn * dn);
+        occ |= hit ? (1u << k) : 0u;
+      }
     }
     if (occ == FULL) return 0;
   }
@@ -337,7 +551,7 @@ __device__ __forceinline__ int shadow_lit_count(const FastScene &sc, V3<float> s
 #pragma unroll
     for (int k = 0; k < CH; k++) {
       if ((occ >> k) & 1u) continue;
-      const float a = dd[k];
+      const float a = dd_of(k);
       const float b = 2.0f * fmaf(j.jx(k), L.x, fmaf(j.jy(k), L.y, fmaf(j.jz(k), L.z, Lr)));
       const float disc = b * b - 4.0f * a * c;
       if (disc < 0.0f) continue;

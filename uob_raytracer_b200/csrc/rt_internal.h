@@ -69,7 +69,7 @@ size_t brute_smem_bytes(int n, int n_sh);
 // dynamic shared memory the fast kernels need on top of the scene (parked primary hits + jitter columns) for S shadow samples
 size_t fast_extra_smem(int S);
 // static shared memory of the draw kernels (per-warp caster lists, counters), rounded up
-constexpr size_t kDrawStaticSmem = 4608;
+constexpr size_t kDrawStaticSmem = 6144;  // the mixed kernel carries the statics of both lane mappings (5.2 KB)
 // rt_peak.cu (small utility kernels)
 cudaError_t launch_peer_signal(uint32_t *flag, uint32_t value, cudaStream_t stream);
 cudaError_t launch_peer_wait(const uint32_t *flags, int n, uint32_t value, int *status, cudaStream_t stream);

@@ -32,6 +32,7 @@ __device__ __forceinline__ SceneView stage_scene(float4 *smem, const float4 *__r
   sc.sa = smem + 5 * n;
   sc.sb = sc.sa + n_sh;
   sc.sc = sc.sb + n_sh;
+  sc.tnd = nullptr;
   sc.n = n;
   sc.n_sh = n_sh;
   return sc;
@@ -56,9 +57,14 @@ __device__ __forceinline__ bool tile_of_block(const FrameParams &p, int block, i
       return false;  // rendered as part of rectangle 0
     return true;
   } else {
-    if (p.tile_order) gb = p.tile_order[gb];
-    by = gb / p.grid_x;
-    bx = gb - by * p.grid_x;
+    if (p.tile_order) {  // launch-order table: tile coordinates packed as by << 16 | bx (no division per block)
+      const int t = p.tile_order[gb];
+      by = t >> 16;
+      bx = t & 0xffff;
+    } else {
+      by = gb / p.grid_x;
+      bx = gb - by * p.grid_x;
+    }
     if constexpr (MIXED) {  // tiles inside a sphere rectangle belong to the split blocks
       for (int r = 0; r < p.n_rect; r++)
         if (bx >= p.rect[r][0] && bx < p.rect[r][2] && by >= p.rect[r][1] && by < p.rect[r][3]) return false;
@@ -104,7 +110,7 @@ SplitMode split_mode(const rt_ctx *ctx, const FrameParams &fp);
 int sphere_rects(FrameParams &fp);
 
 // float4 slots of the scene part of the fast kernel's shared memory (see brute_smem_bytes)
-__host__ __device__ inline int scene_smem_float4(int n, int n_sh) { return 8 * n + 5 * n_sh + (n + n_sh + 3) / 4 + 1; }
+__host__ __device__ inline int scene_smem_float4(int n, int n_sh) { return 12 * n + 5 * n_sh + (n + n_sh + 3) / 4 + 1; }
 
 // extra_smem: dynamic shared memory beyond the scene (fast kernels: fast_extra_smem); name: what rt_last_kernel_name reports
 template <class K>
