@@ -57,7 +57,9 @@ enum {
   RT_FLAG_NO_SPLIT = 1u << 6,
   /* Four lanes per pixel only for the tiles that can see a sphere (the pixels with mirror / glass bounce chains), ordinary
    * mapping elsewhere, in one launch.  What the default chooses for small launches. */
-  RT_FLAG_SPLIT_HEAVY = 1u << 7
+  RT_FLAG_SPLIT_HEAVY = 1u << 7,
+  /* rt_stream_wait_geq / rt_stream_write use one-warp kernels instead of the driver's stream memory operations */
+  RT_FLAG_NO_STREAM_MEMOPS = 1u << 8
 };
 
 /* Everything that is a compile-time constant in the reference
@@ -158,8 +160,8 @@ uint64_t rt_kernel_launches(const rt_ctx *ctx);
 const char *rt_scene_mode(const rt_ctx *ctx);
 
 /* Name of the draw kernel instantiation the last render call launched, e.g.
- * "draw_fast_kernel<8,true,false,false>" (shadow chunk, S == chunk, strict, split) or "draw_fast_mixed_kernel<10,true,false>"
- * — what bench.py prints as roofline.kernel and what the tests pin the benchmarked instantiation with.  "" before the
+ * "draw_fast_kernel<8,true,false,plain>" (shadow chunk, S == chunk, strict arithmetic, lane mapping: plain / split / mixed)
+ * or "draw_bvh_kernel<float,8>" — what bench.py prints as roofline.kernel and what the tests pin the benchmarked instantiation with.  "" before the
  * first launch.  Diagnostic; no reference counterpart. */
 const char *rt_last_kernel_name(const rt_ctx *ctx);
 
@@ -211,6 +213,21 @@ int rt_peer_wait(rt_ctx *ctx, const uint32_t *dev_flags, int n, uint32_t value, 
  * a device-local copy of the flag and only the first ones poll the owner's memory.  One launch, then cleared.
  * No reference counterpart (the reference has one device and one in-order queue, skeleton.cpp:388). */
 int rt_gate_next_frame(rt_ctx *ctx, const uint32_t *dev_flag, uint32_t value);
+
+/* Double-buffered hand-over.  A context owns TWO frame slots in one allocation (so one IPC handle maps both): slot s
+ * starts rt_frame_slot_words(ctx) * s words behind rt_device_frame(ctx) and is followed by its own RT_PEER_FLAGS words.
+ * Frame f goes to slot f & 1, so the peers may store frame f + 1 while the owner still reads frame f back.
+ *   rt_signal_after_frame: the next draw launch of this context ends with "all my pixels are visible system-wide, then
+ *                          *dev_counter += 1" — done by the last block of the draw kernel itself, no extra launch.  The
+ *                          owner waits for the count of deliveries: (ranks - 1) per frame that used the slot.
+ *   rt_stream_wait_geq:    stream-ordered wait until *dev_word >= value  (driver stream memory operation, no kernel)
+ *   rt_stream_write:       stream-ordered *dev_word = value after everything queued before it (e.g. "slot consumed")
+ * No reference counterpart (one device, one in-order queue: skeleton.cpp:388). */
+size_t rt_frame_slot_words(const rt_ctx *ctx);
+int rt_signal_after_frame(rt_ctx *ctx, uint32_t *dev_counter);
+int rt_stream_wait_geq(rt_ctx *ctx, const uint32_t *dev_word, uint32_t value, void *stream);
+int rt_stream_write(rt_ctx *ctx, uint32_t *dev_word, uint32_t value, void *stream);
+int rt_read_frame_slot(rt_ctx *ctx, int slot, uint32_t *host_argb);
 
 /* Host-side launch planning, exposed for the CPU test suite (pure functions: no context, no device).  No reference
  * counterpart — the reference launches one work-item per pixel over the whole frame (skeleton.cpp:170-172).

@@ -76,6 +76,10 @@ def report(seed, verbose=True):
             f">16: {int(off16.sum()):4d} (bounce {int((off16 & bounce_px).sum()):4d})  bounce px share {100 * bounce_px.mean():5.1f}%")
     if verbose:
         print(line, flush=True)
+    if os.environ.get("FUZZ_DUMP"):
+        np.savez_compressed(os.path.join(ROOT, "gpurun_out", f"fuzz_{seed}_{os.environ['FUZZ_DUMP']}.npz"), fast=fast, strict=strict,
+                            bounce_px=bounce_px, verts=scene.verts, normals=scene.normals, colors=scene.colors,
+                            meta=np.array([m["W"], m["H"], m["aa"], m["shadow_samples"], m["max_bounces"], m["focal"], *m["cam"], *m["light"], m["yaw"], m["pitch"]], np.float64))
     return float(off1.mean()), line
 
 

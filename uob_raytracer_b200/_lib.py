@@ -28,6 +28,7 @@ RT_FLAG_REFERENCE_LOOPS = 1 << 4
 RT_FLAG_SPLIT_PIXELS = 1 << 5
 RT_FLAG_NO_SPLIT = 1 << 6
 RT_FLAG_SPLIT_HEAVY = 1 << 7
+RT_FLAG_NO_STREAM_MEMOPS = 1 << 8
 
 
 class RtConfig(ctypes.Structure):
@@ -69,6 +70,11 @@ RT_SYMBOLS = {
     "rt_peer_signal": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_uint32, ctypes.c_void_p]),
     "rt_peer_wait": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_uint32, ctypes.c_void_p]),
     "rt_gate_next_frame": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_uint32]),
+    "rt_frame_slot_words": (ctypes.c_size_t, [ctypes.c_void_p]),
+    "rt_signal_after_frame": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p]),
+    "rt_stream_wait_geq": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_uint32, ctypes.c_void_p]),
+    "rt_stream_write": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_uint32, ctypes.c_void_p]),
+    "rt_read_frame_slot": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p]),
     "rt_debug_visible_rect": (ctypes.c_int, [ctypes.c_void_p, c_float_p, c_float_p, c_float_p, c_float_p, ctypes.c_float,
                                              ctypes.POINTER(ctypes.c_int)]),
     "rt_debug_tile_lists": (ctypes.c_int, [ctypes.c_void_p, c_float_p, c_float_p, ctypes.c_float, ctypes.POINTER(ctypes.c_int), ctypes.c_int,

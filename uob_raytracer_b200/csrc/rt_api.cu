@@ -137,49 +137,152 @@ static void visible_rect_of(const float scene_lo[3], const float scene_hi[3], Fr
 // The rectangles only steer performance — either lane mapping renders any tile correctly — so nothing here needs to be
 // conservative; two pixels of margin keep the silhouette inside anyway.  Pure arithmetic, redone for every launch: a
 // moving camera costs nothing (no tables, no copies, no synchronisation).
+// Pixel rectangle {x0, y0, x1, y1} (half-open, two pixels of margin, clipped to the frame) of sphere i for this camera.
+// 0: no primary ray can reach the sphere (behind the camera or outside the frame); 1: bounded; 2: not bounded (the camera
+// plane cuts the sphere, the camera sits inside it, or the rotation matrix cannot be inverted) — rect = the whole frame.
+static int sphere_pixel_rect(const FrameParams &fp, const double inv[9], bool have_inv, int i, int rect[4]) {
+  rect[0] = 0;
+  rect[1] = 0;
+  rect[2] = fp.W;
+  rect[3] = fp.H;
+  if (!have_inv) return 2;
+  const double P[3] = {(double)rt::kSphereCenterR2[i][0] - fp.cam[0], (double)rt::kSphereCenterR2[i][1] - fp.cam[1],
+                       (double)rt::kSphereCenterR2[i][2] - fp.cam[2]};
+  const double cx = inv[0] * P[0] + inv[1] * P[1] + inv[2] * P[2], cy = inv[3] * P[0] + inv[4] * P[1] + inv[5] * P[2],
+               cz = inv[6] * P[0] + inv[7] * P[1] + inv[8] * P[2];
+  const double r = sqrt((double)rt::kSphereCenterR2[i][3]) * 1.001;
+  if (!(cz == cz) || !(cx == cx) || !(cy == cy)) return 2;
+  if (cz <= -r) {  // wholly behind the camera: no primary ray (t >= 0) reaches it
+    rect[2] = rect[0];
+    rect[3] = rect[1];
+    return 0;
+  }
+  if (!(cz > r * 1.001)) return 2;
+  const double den = cz * cz - r * r;
+  const double sx = r * sqrt(cx * cx + den), sy = r * sqrt(cy * cy + den);
+  const double kx0 = (cx * cz - sx) / den, kx1 = (cx * cz + sx) / den, ky0 = (cy * cz - sy) / den, ky1 = (cy * cz + sy) / den;
+  // sub-pixel coordinate v = f k; pixel = (v + W A / 2) / A
+  const double px0 = (fp.focal * kx0 + 0.5 * fp.W * fp.A) / fp.A, px1 = (fp.focal * kx1 + 0.5 * fp.W * fp.A) / fp.A;
+  const double py0 = (fp.focal * ky0 + 0.5 * fp.H * fp.A) / fp.A, py1 = (fp.focal * ky1 + 0.5 * fp.H * fp.A) / fp.A;
+  if (!(fabs(px0) < 1e9 && fabs(px1) < 1e9 && fabs(py0) < 1e9 && fabs(py1) < 1e9)) return 2;
+  const double x0 = fmax(0.0, floor(px0) - 2.0), x1 = fmin((double)fp.W, floor(px1) + 3.0);
+  const double y0 = fmax(0.0, floor(py0) - 2.0), y1 = fmin((double)fp.H, floor(py1) + 3.0);
+  if (!(x0 < x1 && y0 < y1)) {
+    rect[2] = rect[0];
+    rect[3] = rect[1];
+    return 0;
+  }
+  rect[0] = (int)x0;
+  rect[1] = (int)y0;
+  rect[2] = (int)x1;
+  rect[3] = (int)y1;
+  return 1;
+}
+
 int sphere_rects(FrameParams &fp) {
   const int gx = (fp.W + kTileW - 1) / kTileW, gy = (fp.rows + kTileH - 1) / kTileH;
   fp.n_rect = 0;
   fp.rect_first[0] = fp.rect_first[1] = 0;
-  auto whole = [&]() {
-    fp.n_rect = 1;
-    fp.rect[0][0] = 0;
-    fp.rect[0][1] = 0;
-    fp.rect[0][2] = gx;
-    fp.rect[0][3] = gy;
-    return 4 * gx * gy;
-  };
   double inv[9];
-  if (!inverse_rotation(fp, inv)) return whole();
+  const bool have_inv = inverse_rotation(fp, inv);
   int total = 0;
   for (int i = 0; i < RT_SPHERES; i++) {
-    const double P[3] = {(double)rt::kSphereCenterR2[i][0] - fp.cam[0], (double)rt::kSphereCenterR2[i][1] - fp.cam[1],
-                         (double)rt::kSphereCenterR2[i][2] - fp.cam[2]};
-    const double cx = inv[0] * P[0] + inv[1] * P[1] + inv[2] * P[2], cy = inv[3] * P[0] + inv[4] * P[1] + inv[5] * P[2],
-                 cz = inv[6] * P[0] + inv[7] * P[1] + inv[8] * P[2];
-    const double r = sqrt((double)rt::kSphereCenterR2[i][3]) * 1.001;
-    if (!(cz > -r)) continue;            // wholly behind the camera: no primary ray sees it
-    if (!(cz > r * 1.001)) return whole();  // the camera plane cuts the sphere (or the camera is inside it)
-    const double den = cz * cz - r * r;
-    const double sx = r * sqrt(cx * cx + den), sy = r * sqrt(cy * cy + den);
-    const double kx0 = (cx * cz - sx) / den, kx1 = (cx * cz + sx) / den, ky0 = (cy * cz - sy) / den, ky1 = (cy * cz + sy) / den;
-    // sub-pixel coordinate v = f k; pixel = (v + W A / 2) / A
-    const double px0 = (fp.focal * kx0 + 0.5 * fp.W * fp.A) / fp.A, px1 = (fp.focal * kx1 + 0.5 * fp.W * fp.A) / fp.A;
-    const double py0 = (fp.focal * ky0 + 0.5 * fp.H * fp.A) / fp.A, py1 = (fp.focal * ky1 + 0.5 * fp.H * fp.A) / fp.A;
-    if (!(fabs(px0) < 1e9 && fabs(px1) < 1e9 && fabs(py0) < 1e9 && fabs(py1) < 1e9)) return whole();
-    const double x0 = fmax(0.0, floor(px0) - 2.0), x1 = fmin((double)fp.W, floor(px1) + 3.0);
-    const double y0 = fmax((double)fp.row0, floor(py0) - 2.0), y1 = fmin((double)(fp.row0 + fp.rows), floor(py1) + 3.0);
-    if (!(x0 < x1 && y0 < y1)) continue;  // outside the frame or this row range
+    int px[4];
+    const int kind = sphere_pixel_rect(fp, inv, have_inv, i, px);
+    if (kind == 0) continue;
+    if (kind == 2) {  // no bound: the whole launch is one rectangle
+      fp.n_rect = 1;
+      fp.rect[0][0] = 0;
+      fp.rect[0][1] = 0;
+      fp.rect[0][2] = gx;
+      fp.rect[0][3] = gy;
+      fp.rect_first[0] = 0;
+      return 4 * gx * gy;
+    }
+    // clip to this launch's rows and round out to whole tiles of its grid
+    const int y0 = std::max(px[1], fp.row0), y1 = std::min(px[3], fp.row0 + fp.rows);
+    if (y0 >= y1) continue;
     int *q = fp.rect[fp.n_rect];
-    q[0] = (int)x0 / kTileW;
-    q[1] = ((int)y0 - fp.row0) / kTileH;
-    q[2] = std::min(gx, ((int)x1 + kTileW - 1) / kTileW);
-    q[3] = std::min(gy, ((int)y1 - fp.row0 + kTileH - 1) / kTileH);
+    q[0] = px[0] / kTileW;
+    q[1] = (y0 - fp.row0) / kTileH;
+    q[2] = std::min(gx, (px[2] + kTileW - 1) / kTileW);
+    q[3] = std::min(gy, (y1 - fp.row0 + kTileH - 1) / kTileH);
     fp.rect_first[fp.n_rect] = total;
     total += 4 * (q[2] - q[0]) * (q[3] - q[1]);
     fp.n_rect++;
   }
   return total;
+}
+
+// Per-frame host work of the tuned kernels.  The constants of the exact primary test — b = cam - v0, det[b,e1,e2] and the
+// cofactors of det[-d,b,e2], det[-d,e1,b] (rt_fast.cuh) — depend on the camera position only; they are computed here
+// with the reference's single-rounded operation sequence (this file is compiled without FMA contraction; IEEE binary32 on
+// the host is the same arithmetic as the __fmul_rn / __fadd_rn the kernels would use), followed by their affine form for
+// this rotation matrix and focal length.  2 KB for the Cornell box; recomputed and copied only when the camera moves.
+cudaError_t prepare_frame(rt_ctx *ctx, FrameParams &fp, cudaStream_t stream) {
+  // longest un-normalised primary ray: a corner ray of the frame
+  {
+    const float hx = 0.5f * (float)fp.W * (float)fp.A, hy = 0.5f * (float)fp.H * (float)fp.A;
+    float dmax = 0.0f;
+    for (int c = 0; c < 4; c++) {
+      const float vx = (c & 1) ? hx : -hx, vy = (c & 2) ? hy : -hy;
+      float d2 = 0.0f;
+      for (int r = 0; r < 3; r++) {
+        const float d = fp.rot[3 * r] * vx + fp.rot[3 * r + 1] * vy + fp.rot[3 * r + 2] * fp.focal;
+        d2 += d * d;
+      }
+      dmax = fmaxf(dmax, sqrtf(d2));
+    }
+    fp.dmax = dmax * 1.001f;
+  }
+  double inv[9];
+  const bool have_inv = inverse_rotation(fp, inv);
+  for (int i = 0; i < RT_SPHERES; i++) sphere_pixel_rect(fp, inv, have_inv, i, fp.sph_px[i]);
+  if (ctx->use_bvh || ctx->n == 0) return cudaSuccess;
+  float key[14] = {fp.rot[0], fp.rot[1], fp.rot[2], fp.rot[3], fp.rot[4], fp.rot[5], fp.rot[6], fp.rot[7], fp.rot[8],
+                   fp.cam[0], fp.cam[1], fp.cam[2], fp.focal, fp.dmax};
+  if (ctx->fconst_valid && memcmp(key, ctx->fconst_key, sizeof key) == 0) return cudaSuccess;
+  const int n = ctx->n;
+  const float4 *ta = ctx->h_tri.data(), *tb = ta + n, *tc = tb + n;
+  ctx->h_fconst.resize(6 * (size_t)n);
+  float4 *prim = ctx->h_fconst.data(), *aff = prim + 3 * (size_t)n;
+  const float *R = fp.rot;
+  for (int i = 0; i < n; i++) {
+    const float4 A = ta[i], Bq = tb[i], C = tc[i];
+    // rt_fast.cuh: primary_constants, operation for operation
+    const float bx = fp.cam[0] - A.x, by = fp.cam[1] - A.y, bz = fp.cam[2] - A.z;
+    const float p0 = bx * A.w, p1 = by * Bq.w, p2 = bz * C.w;
+    const float detA0 = (p0 - p1) + p2;
+    const float u0a = by * C.z, u0b = bz * C.y, u1a = bx * C.z, u1b = bz * C.x, u2a = bx * C.y, u2b = by * C.x;
+    const float U0 = u0a - u0b, U1 = u1a - u1b, U2 = u2a - u2b;
+    const float v0a = Bq.y * bz, v0b = Bq.z * by, v1a = Bq.x * bz, v1b = Bq.z * bx, v2a = Bq.x * by, v2b = Bq.y * bx;
+    const float V0 = v0a - v0b, V1 = v1a - v1b, V2 = v2a - v2b;
+    const float l1 = fmaxf(fmaxf(fabsf(U0) + fabsf(U1) + fabsf(U2), fabsf(V0) + fabsf(V1) + fabsf(V2)), fabsf(A.w) + fabsf(Bq.w) + fabsf(C.w));
+    const float tol = 2e-6f * l1;
+    prim[3 * i + 0] = make_float4(A.w, Bq.w, C.w, detA0);
+    prim[3 * i + 1] = make_float4(U0, U1, U2, tol);
+    prim[3 * i + 2] = make_float4(V0, V1, V2, 3.0f * tol);
+    // rt_fast.cuh: primary_affine — R^T (x, -y, z), third component times f; tau = 2 tol dmax
+    auto g = [&](float x, float y, float z, float w) {
+      y = -y;
+      return make_float4(R[0] * x + R[3] * y + R[6] * z, R[1] * x + R[4] * y + R[7] * z, (R[2] * x + R[5] * y + R[8] * z) * fp.focal, w);
+    };
+    aff[3 * i + 0] = g(A.w, Bq.w, C.w, detA0);
+    aff[3 * i + 1] = g(U0, U1, U2, tol * 2.0f * fp.dmax);
+    aff[3 * i + 2] = g(V0, V1, V2, 0.0f);
+  }
+  // the buffer may still be read by launches of the previous camera on another stream
+  if (ctx->fconst_valid && ctx->fconst_stream != stream) {
+    cudaError_t e = cudaStreamSynchronize(ctx->fconst_stream);
+    if (e != cudaSuccess) return e;
+  }
+  // pageable source: staged before the call returns, and ordered before the launch on the stream
+  cudaError_t e = cudaMemcpyAsync(ctx->d_fconst, ctx->h_fconst.data(), sizeof(float4) * ctx->h_fconst.size(), cudaMemcpyHostToDevice, stream);
+  if (e != cudaSuccess) return e;
+  memcpy(ctx->fconst_key, key, sizeof key);
+  ctx->fconst_valid = true;
+  ctx->fconst_stream = stream;
+  return cudaSuccess;
 }
 
 // centre-out launch order of the tile grid of rows [row0, row0 + rows) (pure host code)
@@ -253,6 +356,8 @@ static int free_ctx(rt_ctx *ctx) {
   if (ctx->own_stream && ctx->own_stream != ctx->stream) cudaStreamSynchronize(ctx->own_stream);
   if (ctx->d_frame) cudaFree(ctx->d_frame);
   if (ctx->d_scene) cudaFree(ctx->d_scene);
+  if (ctx->d_fconst) cudaFree(ctx->d_fconst);
+  if (ctx->d_work) cudaFree(ctx->d_work);
   if (ctx->d_ray_counters) cudaFree(ctx->d_ray_counters);
   if (ctx->d_wait_status) cudaFree(ctx->d_wait_status);
   if (ctx->d_gate_seen) cudaFree(ctx->d_gate_seen);
@@ -271,7 +376,6 @@ static int free_ctx(rt_ctx *ctx) {
     if (ctx->slot_kernel_done[sl]) cudaEventDestroy(ctx->slot_kernel_done[sl]);
     if (ctx->slot_copy_done[sl]) cudaEventDestroy(ctx->slot_copy_done[sl]);
   }
-  if (ctx->d_frame_alt) cudaFree(ctx->d_frame_alt);
   if (ctx->ev0) cudaEventDestroy(ctx->ev0);
   if (ctx->ev1) cudaEventDestroy(ctx->ev1);
   if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
@@ -346,10 +450,16 @@ rt_ctx *rt_create(const rt_config *cfg) {
   }
   if ((e = cudaEventCreateWithFlags(&ctx->band_start, cudaEventDisableTiming)) != cudaSuccess) return fail("creating event", e);
   // the frame, followed by RT_PEER_FLAGS hand-over flags (same allocation, so one IPC handle maps both)
-  const size_t frame_words = (size_t)cfg->width * cfg->height + RT_PEER_FLAGS;
+  // two frame slots, each followed by RT_PEER_FLAGS hand-over flags — ONE allocation, so one IPC handle maps everything a
+  // peer GPU needs: slot s starts at rt_frame_slot_words() * s words.  Slot 0 is "the" frame; slot 1 is the second frame
+  // in flight of rt_render_begin and the other half of a double-buffered multi-GPU hand-over.
+  const size_t frame_words = 2 * ((size_t)cfg->width * cfg->height + RT_PEER_FLAGS);
   if ((e = cudaMalloc(&ctx->d_frame, sizeof(uint32_t) * frame_words)) != cudaSuccess) return fail("creating screen buffer", e);
-  if ((e = cudaMalloc(&ctx->d_gate_seen, sizeof(uint32_t))) != cudaSuccess) return fail("creating gate flag copy", e);
-  if ((e = cudaMemsetAsync(ctx->d_gate_seen, 0, sizeof(uint32_t), ctx->stream)) != cudaSuccess) return fail("clearing gate flag copy", e);
+  ctx->d_frame_alt = ctx->d_frame + frame_words / 2;
+  if ((e = cudaMalloc(&ctx->d_gate_seen, 2 * sizeof(uint32_t))) != cudaSuccess) return fail("creating gate flag copy", e);
+  if ((e = cudaMemsetAsync(ctx->d_gate_seen, 0, 2 * sizeof(uint32_t), ctx->stream)) != cudaSuccess) return fail("clearing gate flag copy", e);
+  if ((e = cudaMalloc(&ctx->d_work, 2 * sizeof(unsigned) * rt_ctx::kWorkSlots)) != cudaSuccess) return fail("creating work counters", e);
+  if ((e = cudaMemsetAsync(ctx->d_work, 0, 2 * sizeof(unsigned) * rt_ctx::kWorkSlots, ctx->stream)) != cudaSuccess) return fail("clearing work counters", e);
   if ((e = cudaMalloc(&ctx->d_wait_status, sizeof(int))) != cudaSuccess) return fail("creating wait status", e);
   if ((e = cudaMemsetAsync(ctx->d_wait_status, 0, sizeof(int), ctx->stream)) != cudaSuccess) return fail("clearing wait status", e);
   if (cfg->flags & RT_FLAG_COUNT_RAYS) {
@@ -465,10 +575,17 @@ int rt_upload_scene(rt_ctx *ctx, const float *verts, const float *normals, const
     }
   }
   if (ctx->d_scene) {
-    RT_CUDA(ctx, cudaStreamSynchronize(ctx->stream), "waiting before scene replacement");
+    RT_CUDA(ctx, cudaDeviceSynchronize(), "waiting before scene replacement");
     RT_CUDA(ctx, cudaFree(ctx->d_scene), "releasing triangle buffer");
     ctx->d_scene = nullptr;
   }
+  if (ctx->d_fconst) {
+    RT_CUDA(ctx, cudaFree(ctx->d_fconst), "releasing per-frame constants");
+    ctx->d_fconst = nullptr;
+  }
+  ctx->fconst_valid = false;
+  ctx->h_tri.assign(h.begin(), h.begin() + 3 * (size_t)n);  // ta | tb | tc: what prepare_frame computes the constants from
+  RT_CUDA(ctx, cudaMalloc(&ctx->d_fconst, sizeof(float4) * (size_t)(n ? 6 * n : 1)), "creating per-frame constants");
   RT_CUDA(ctx, cudaMalloc(&ctx->d_scene, sizeof(float4) * (h.size() ? h.size() : 1)), "creating triangle buffer");
   if (!h.empty())
     RT_CUDA(ctx, cudaMemcpyAsync(ctx->d_scene, h.data(), sizeof(float4) * h.size(), cudaMemcpyHostToDevice, ctx->stream),
@@ -479,6 +596,25 @@ int rt_upload_scene(rt_ctx *ctx, const float *verts, const float *normals, const
   ctx->use_bvh = use_bvh;
   ctx->have_scene = true;
   return RT_OK;
+}
+
+// what the reference passes per frame (skeleton.cpp:149-167) plus the context's run-time constants
+static void fill_camera(const rt_ctx *ctx, rt::FrameParams &fp, const float rot12[12], const float cam[4], const float light[4], float focal) {
+  memset(&fp, 0, sizeof fp);
+  fp.W = ctx->cfg.width;
+  fp.H = ctx->cfg.height;
+  fp.row0 = ctx->row0;
+  fp.rows = ctx->rows;
+  fp.A = ctx->cfg.aa;
+  fp.S = ctx->cfg.shadow_samples;
+  fp.B = ctx->cfg.max_bounces;
+  fp.focal = focal;
+  for (int r = 0; r < 3; r++)
+    for (int c = 0; c < 3; c++) fp.rot[3 * r + c] = rot12[4 * r + c];  // float4-strided rows (skeleton.cpp:149-151)
+  for (int c = 0; c < 3; c++) {
+    fp.cam[c] = cam[c];
+    fp.light[c] = light[c];
+  }
 }
 
 static int render_impl(rt_ctx *ctx, const float rot12[12], const float cam[4], const float light[4], float focal,
@@ -494,21 +630,12 @@ static int render_impl(rt_ctx *ctx, const float rot12[12], const float cam[4], c
   }
   RT_CUDA(ctx, cudaSetDevice(ctx->cfg.device), "selecting device");
   rt::FrameParams fp;
-  fp.W = ctx->cfg.width;
-  fp.H = ctx->cfg.height;
+  fill_camera(ctx, fp, rot12, cam, light, focal);
   fp.row0 = band_row0 >= 0 ? band_row0 : ctx->row0;
   fp.rows = band_row0 >= 0 ? band_rows : ctx->rows;
-  fp.A = ctx->cfg.aa;
-  fp.S = ctx->cfg.shadow_samples;
-  fp.B = ctx->cfg.max_bounces;
-  fp.focal = focal;
-  for (int r = 0; r < 3; r++)
-    for (int c = 0; c < 3; c++) fp.rot[3 * r + c] = rot12[4 * r + c];  // float4-strided rows (skeleton.cpp:149-151)
-  for (int c = 0; c < 3; c++) {
-    fp.cam[c] = cam[c];
-    fp.light[c] = light[c];
-  }
   rt::visible_rect(ctx, fp);
+  // per-frame constants for this camera (a band finds them in place: rt_render prepared them in front of the bands)
+  RT_CUDA(ctx, rt::prepare_frame(ctx, fp, stream), "writing per-frame constants");
   // frame gate: the tuned brute-force kernels poll the flag themselves; the other kernels get a wait kernel in front
   fp.gate_flag = nullptr;
   fp.gate_value = 0;
@@ -518,10 +645,15 @@ static int render_impl(rt_ctx *ctx, const float rot12[12], const float cam[4], c
     const bool in_kernel = !ctx->use_bvh && !ctx->d_ray_counters &&
                            !((ctx->cfg.flags & RT_FLAG_STRICT_IEEE) && (ctx->cfg.flags & RT_FLAG_REFERENCE_LOOPS));
     if (in_kernel) {
-      if (ctx->gate_flag != ctx->gate_flag_cached) {  // the device-local copy belongs to another flag
-        RT_CUDA(ctx, cudaMemsetAsync(ctx->d_gate_seen, 0, sizeof(uint32_t), stream), "clearing gate flag copy");
-        ctx->gate_flag_cached = ctx->gate_flag;
+      // device-local copies of the last value seen, one per flag for up to two flags (the two slots of a
+      // double-buffered hand-over alternate between two "consumed" flags)
+      int e = ctx->gate_flag == ctx->gate_flag_cached[0] ? 0 : (ctx->gate_flag == ctx->gate_flag_cached[1] ? 1 : -1);
+      if (e < 0) {
+        e = (int)(ctx->gate_victim++ & 1u);
+        RT_CUDA(ctx, cudaMemsetAsync(ctx->d_gate_seen + e, 0, sizeof(uint32_t), stream), "clearing gate flag copy");
+        ctx->gate_flag_cached[e] = ctx->gate_flag;
       }
+      fp.gate_seen = ctx->d_gate_seen + e;
       fp.gate_flag = ctx->gate_flag;
       fp.gate_value = ctx->gate_value;
     } else {
@@ -531,6 +663,16 @@ static int render_impl(rt_ctx *ctx, const float rot12[12], const float cam[4], c
     ctx->peer_waits = true;
     ctx->gate_flag = nullptr;
   }
+  // rt_signal_after_frame: the tuned kernels add to the counter themselves once the last block is done; the other kernels
+  // get a one-thread kernel behind them
+  uint32_t *signal_after = ctx->signal_flag;
+  ctx->signal_flag = nullptr;
+  fp.signal_flag = nullptr;
+  if (signal_after && !ctx->use_bvh && !ctx->d_ray_counters &&
+      !((ctx->cfg.flags & RT_FLAG_STRICT_IEEE) && (ctx->cfg.flags & RT_FLAG_REFERENCE_LOOPS))) {
+    fp.signal_flag = signal_after;
+    signal_after = nullptr;
+  }
   fp.out = dev_argb ? dev_argb : ctx->d_frame;
   fp.ray_counters = ctx->d_ray_counters;
   if (ctx->d_ray_counters && band_row0 < 0)
@@ -538,6 +680,10 @@ static int render_impl(rt_ctx *ctx, const float rot12[12], const float cam[4], c
   const bool whole = band_row0 < 0;
   if (whole) RT_CUDA(ctx, cudaEventRecord(ctx->ev0, stream), "recording start event");
   RT_CUDA(ctx, ctx->use_bvh ? rt::launch_draw_bvh(ctx, fp, stream) : rt::launch_draw_brute(ctx, fp, stream), "enqueueing draw kernel");
+  if (signal_after) {
+    RT_CUDA(ctx, rt::launch_peer_add(signal_after, stream), "enqueueing peer signal");
+    ctx->launches++;
+  }
   if (whole) {
     RT_CUDA(ctx, cudaEventRecord(ctx->ev1, stream), "recording stop event");
     ctx->timed = true;
@@ -572,6 +718,12 @@ int rt_render(rt_ctx *ctx, const float rot12[12], const float cam[4], const floa
     return RT_OK;
   }
   RT_CUDA(ctx, cudaSetDevice(ctx->cfg.device), "selecting device");
+  if (ctx->have_scene && rot12 && cam && light) {  // (render_impl reports the errors)
+    // the per-frame constants go in on the context's stream, in front of the bands that read them
+    rt::FrameParams fp;
+    fill_camera(ctx, fp, rot12, cam, light, focal);
+    RT_CUDA(ctx, rt::prepare_frame(ctx, fp, ctx->stream), "writing per-frame constants");
+  }
   RT_CUDA(ctx, cudaEventRecord(ctx->ev0, ctx->stream), "recording start event");
   RT_CUDA(ctx, cudaEventRecord(ctx->band_start, ctx->stream), "recording start event");
   int nb = 0;
@@ -629,14 +781,12 @@ int rt_render_begin(rt_ctx *ctx, const float rot12[12], const float cam[4], cons
     return RT_ERR_INVALID;
   }
   RT_CUDA(ctx, cudaSetDevice(ctx->cfg.device), "selecting device");
-  const size_t frame_words = (size_t)ctx->cfg.width * ctx->cfg.height;
-  if (!ctx->copy_stream) {  // first use: second frame buffer, copy stream, events
+  if (!ctx->copy_stream) {  // first use: copy stream, events
     RT_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking), "creating copy stream");
     for (int sl = 0; sl < 2; sl++) {
       RT_CUDA(ctx, cudaEventCreateWithFlags(&ctx->slot_kernel_done[sl], cudaEventDisableTiming), "creating event");
       RT_CUDA(ctx, cudaEventCreateWithFlags(&ctx->slot_copy_done[sl], cudaEventDisableTiming), "creating event");
     }
-    RT_CUDA(ctx, cudaMalloc(&ctx->d_frame_alt, sizeof(uint32_t) * frame_words), "creating second screen buffer");
   }
   const int sl = (int)(ctx->frames_begun & 1);
   uint32_t *dst = sl ? ctx->d_frame_alt : ctx->d_frame;
@@ -668,10 +818,12 @@ int rt_render_end(rt_ctx *ctx) {
   return RT_OK;
 }
 
-int rt_read_frame(rt_ctx *ctx, uint32_t *host_argb) {
-  if (!ctx || !host_argb) return RT_ERR_INVALID;
+int rt_read_frame(rt_ctx *ctx, uint32_t *host_argb) { return rt_read_frame_slot(ctx, 0, host_argb); }
+
+int rt_read_frame_slot(rt_ctx *ctx, int slot, uint32_t *host_argb) {
+  if (!ctx || !host_argb || slot < 0 || slot > 1) return RT_ERR_INVALID;
   RT_CUDA(ctx, cudaSetDevice(ctx->cfg.device), "selecting device");
-  RT_CUDA(ctx, cudaMemcpyAsync(host_argb, ctx->d_frame, sizeof(uint32_t) * (size_t)ctx->cfg.width * ctx->cfg.height,
+  RT_CUDA(ctx, cudaMemcpyAsync(host_argb, ctx->d_frame + rt_frame_slot_words(ctx) * (size_t)slot, sizeof(uint32_t) * (size_t)ctx->cfg.width * ctx->cfg.height,
                                cudaMemcpyDeviceToHost, ctx->stream), "reading screen buffer data");
   RT_CUDA(ctx, cudaStreamSynchronize(ctx->stream), "reading screen buffer data");
   return RT_OK;
@@ -850,6 +1002,56 @@ int rt_gate_next_frame(rt_ctx *ctx, const uint32_t *dev_flag, uint32_t value) {
 }
 
 uint32_t *rt_device_frame(rt_ctx *ctx) { return ctx ? ctx->d_frame : nullptr; }
+
+size_t rt_frame_slot_words(const rt_ctx *ctx) { return ctx ? (size_t)ctx->cfg.width * ctx->cfg.height + RT_PEER_FLAGS : 0; }
+
+int rt_signal_after_frame(rt_ctx *ctx, uint32_t *dev_counter) {
+  if (!ctx || !dev_counter) return RT_ERR_INVALID;
+  ctx->signal_flag = dev_counter;
+  return RT_OK;
+}
+
+// Stream-ordered wait / write on a 32-bit word without a kernel: the driver's stream memory operations
+// (cuStreamWaitValue32 / cuStreamWriteValue32), resolved through the runtime so that the library does not link libcuda.
+typedef int (*stream_memop_fn)(void *stream, unsigned long long addr, unsigned value, unsigned flags);
+static stream_memop_fn driver_memop(const char *name) {
+  void *fn = nullptr;
+  cudaDriverEntryPointQueryResult q;
+  if (cudaGetDriverEntryPoint(name, &fn, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess) {
+    cudaGetLastError();
+    return nullptr;
+  }
+  return (stream_memop_fn)fn;
+}
+
+int rt_stream_wait_geq(rt_ctx *ctx, const uint32_t *dev_word, uint32_t value, void *stream) {
+  if (!ctx || !dev_word) return RT_ERR_INVALID;
+  RT_CUDA(ctx, cudaSetDevice(ctx->cfg.device), "selecting device");
+  cudaStream_t st = stream ? (cudaStream_t)stream : ctx->stream;
+  static stream_memop_fn wait32 = driver_memop("cuStreamWaitValue32");
+  if (wait32 && !(ctx->cfg.flags & RT_FLAG_NO_STREAM_MEMOPS)) {
+    const int rc = wait32(st, (unsigned long long)(uintptr_t)dev_word, value, 0x0 /* CU_STREAM_WAIT_VALUE_GEQ */);
+    if (rc == 0) return RT_OK;
+  }
+  RT_CUDA(ctx, rt::launch_peer_wait(dev_word, 1, value, ctx->d_wait_status, st), "enqueueing peer wait");
+  ctx->launches++;
+  ctx->peer_waits = true;
+  return RT_OK;
+}
+
+int rt_stream_write(rt_ctx *ctx, uint32_t *dev_word, uint32_t value, void *stream) {
+  if (!ctx || !dev_word) return RT_ERR_INVALID;
+  RT_CUDA(ctx, cudaSetDevice(ctx->cfg.device), "selecting device");
+  cudaStream_t st = stream ? (cudaStream_t)stream : ctx->stream;
+  static stream_memop_fn write32 = driver_memop("cuStreamWriteValue32");
+  if (write32 && !(ctx->cfg.flags & RT_FLAG_NO_STREAM_MEMOPS)) {
+    const int rc = write32(st, (unsigned long long)(uintptr_t)dev_word, value, 0x0 /* CU_STREAM_WRITE_VALUE_DEFAULT: memory barrier in front */);
+    if (rc == 0) return RT_OK;
+  }
+  RT_CUDA(ctx, rt::launch_peer_signal(dev_word, value, st), "enqueueing peer signal");
+  ctx->launches++;
+  return RT_OK;
+}
 
 float rt_last_kernel_ms(rt_ctx *ctx) {
   if (!ctx || !ctx->timed) return -1.0f;

@@ -25,12 +25,12 @@ __global__ void __launch_bounds__(kThreads) draw_brute_kernel(const __grid_const
 }
 
 // strict kernel: 5n + 3n_sh float4; fast kernel: 5n (generic) + 3n (primary constants) + 3n (their affine form) + 5n_sh (shadow records and
-// bounds) + n (plane records of the bounce rays) float4 + n ints (binned triangle list) + n_sh ints (identity caster list)
+// bounds) + n (plane records of the bounce rays) float4 + 8n ints (one binned triangle list per warp) + n_sh ints (identity caster list)
 size_t brute_smem_bytes(int n, int n_sh) { return sizeof(float4) * (size_t)scene_smem_float4(n, n_sh); }
 // what launch_fast_ch<CH> adds for the chunk size RT_DISPATCH_CH picks for S shadow samples
 size_t fast_extra_smem(int S) {
   const int ch = S % 10 == 0 ? 10 : S % 8 == 0 ? 8 : S % 5 == 0 ? 5 : S % 4 == 0 ? 4 : S % 2 == 0 ? 2 : 1;
-  return sizeof(float) * (size_t)(3 * ch + 4 * 7) * kThreads;
+  return sizeof(float) * (size_t)(3 * ch + 4 * 7) * kFastThreads;
 }
 
 // Shadow samples are processed CH at a time (fully unrolled): the largest chunk that divides S, so

@@ -1,6 +1,19 @@
 // rt_draw_fast.cu — the fast `draw` kernel (see rt_fast.cuh for the method).  Compiled once per
 // shadow chunk size: -DRT_FAST_CH=n gives launch_fast_ch<n>.
+#include <stdio.h>
+
 #include "rt_launch.cuh"
+
+// A/B switches of the round-2 prologue work
+#ifndef RT_HOST_CONSTS
+#define RT_HOST_CONSTS 1
+#endif
+#ifndef RT_SPH_RECT
+#define RT_SPH_RECT 1
+#endif
+#ifndef RT_UV_AFFINE
+#define RT_UV_AFFINE 1
+#endif
 
 #ifndef RT_FAST_CH
 #define RT_FAST_CH 8
@@ -14,6 +27,44 @@ constexpr bool kLazyPrimary = false;
 constexpr bool kLazyPrimary = true;
 #endif
 
+#ifndef RT_COOP_RAYS  // a warp with at most this many live bounce rays searches them cooperatively (rt_fast.cuh)
+#define RT_COOP_RAYS 8
+#endif
+
+// secondary_light's bounce loop (kernels.cl:342-365) in warp-synchronous form, for the launches that are too small to
+// fill the GPU (a share of a frame on several GPUs: they end with the longest bounce chain of a single ray).  Called by
+// ALL lanes of warp_mask; follows every lane's mirror / glass hit to the diffuse surface it ends on (id = -1: nothing, or
+// out of bounces — black).  Every round the lanes holding a mirror / glass hit form their next ray and a ballot counts
+// them: few live rays are searched cooperatively by the whole warp — ray compaction across bounces, rt_fast.cuh:
+// closest_triangles_coop — many by their own lanes side by side.  Same arithmetic and same winner either way.
+template <class T>
+__device__ __forceinline__ void resolve_bounces_coop(const FrameParams &p, const SceneView &g, unsigned warp_mask, HitRec<T> &hit, V3<T> dir) {
+  float medium = RT_AIR;
+  int bounce = 0;
+  for (;;) {
+    const bool specular = hit.id != -1 && hit.color.w <= 0.0f;
+    const bool want = specular && bounce < p.B;
+    if (specular && !want) hit.id = -1;  // out of bounces: black (kernels.cl:364)
+    V3<T> start(T(0.0f), T(0.0f), T(0.0f));
+    if (want) {
+      bounce++;
+      V3<T> ndir;
+      if (hit.color.w == 0.0f) reflect_ray<T>(dir, hit.normal, hit.point, start, ndir, medium);
+      else refract_ray<T>(dir, hit.normal, hit.point, medium, start, ndir, medium);
+      dir = ndir;
+      hit.id = -1;
+      hit.color.w = 1.0f;
+    }
+    const unsigned live = __ballot_sync(warp_mask, want);
+    if (live == 0u) break;
+    ClosestState<T> cs;
+    cs.reset();
+    if (__popc(live) <= RT_COOP_RAYS) closest_triangles_coop<T>(g, warp_mask, live, start, dir, cs);
+    else if (want) closest_triangles(g, start, dir, cs);
+    if (want) finish_closest<T>(g, start, dir, cs, hit);
+  }
+}
+
 // CH shadow samples per chunk, SINGLE = (S == CH).  STRICT = RT_FLAG_STRICT_IEEE: same binning, culls and
 // caster lists, but every test that survives them — and all shading arithmetic — runs the reference's exact
 // operation sequence, so the frame is bit-identical to the reference's (and to draw_brute_kernel<sfloat>).
@@ -22,12 +73,15 @@ constexpr bool kLazyPrimary = true;
 // frame; used when a launch is too small to fill the GPU (a 1/4 or 1/8 share of a 1080p frame): the launch then ends
 // with its slowest pixel, a glass-sphere pixel whose A*A rays x several bounces form one serial chain — split four
 // ways.  Per-ray contributions are parked and summed in the reference's ray order, so STRICT stays bit-identical.
-template <int CH, bool SINGLE, bool STRICT, bool SPLIT>
-__device__ __forceinline__ void draw_fast_body(const FrameParams &p, const float4 *__restrict__ scene, int n, int n_sh, int bx, int by) {
+template <int CH, bool SINGLE, bool STRICT, bool SPLIT, bool COOP>
+__device__ __forceinline__ void draw_fast_body(const FrameParams &p, const float4 *__restrict__ scene, const float4 *__restrict__ fconst, int n, int n_sh,
+                                               int bx, int by) {
   extern __shared__ float4 smem[];
   __shared__ int s_warp_count[kThreads / 32];
   __shared__ int s_base;
+#if !RT_SPH_RECT
   __shared__ int s_spheres_visible;
+#endif
   __shared__ int s_wlist[kThreads / 32][kWarpListMax];  // per-warp shadow caster lists
 
   if (p.gate_flag) {
@@ -77,6 +131,13 @@ __device__ __forceinline__ void draw_fast_body(const FrameParams &p, const float
   float *const rec_base = reinterpret_cast<float *>(smem + scene_smem_float4(n, n_sh));
   float *const jit_base = rec_base + 4 * 7 * kThreads;
   for (int i = threadIdx.x; i < 5 * n; i += kThreads) gen[i] = scene[i];
+  // Per-frame triangle constants: the bit-exact kernels take them from the host (rt_api.cu: prepare_frame — the same
+  // single-rounded operations, done once per frame instead of once per block: 0.32 -> 0.30 ms on cfg2); the fast kernels
+  // compute them in the block prologue as before — measured: the extra pointer and loads cost them 64 bytes more stack
+  // (they are register-bound at 80 registers, three blocks per SM) and 5 % (cfg2) to 17 % (cfg3) of their speed.
+  constexpr bool kHC = STRICT && RT_HOST_CONSTS;
+  if constexpr (kHC)
+    for (int i = threadIdx.x; i < 6 * n; i += kThreads) prim[i] = fconst[i];
   for (int i = threadIdx.x; i < 5 * n_sh + n; i += kThreads) shad[i] = scene[5 * n + 3 * n_sh + i];  // records, bounding spheres, plane records
   for (int i = threadIdx.x; i < n_sh; i += kThreads) full_list[i] = i;
   FastScene sc;
@@ -116,6 +177,8 @@ __device__ __forceinline__ void draw_fast_body(const FrameParams &p, const float
       dmax = fmaxf(dmax, sqrtf(dot(dc[c], dc[c])));
     }
     dmax *= 1.001f;
+    if constexpr (kHC) dmax = p.dmax;  // the host's constants carry the frame-wide tolerance
+#if !RT_SPH_RECT
     if (threadIdx.x == 0) {
       // Can any primary ray of the tile hit a sphere?  The tile's rays lie in a cone of half-angle th_t
       // around the centre ray; a sphere is seen from the camera inside a cone of half-angle th_s around
@@ -143,12 +206,15 @@ __device__ __forceinline__ void draw_fast_body(const FrameParams &p, const float
       }
       s_spheres_visible = vis;
     }
+#endif
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (small_scene) {
       bool keep = false;
       if (lane < n) {
-        primary_constants(sc.g, prim, cam, lane);
-        if constexpr (!STRICT) primary_affine(prim, aff, lane, p.rot, p.focal, dmax);
+        if constexpr (!kHC) {
+          primary_constants(sc.g, prim, cam, lane);
+          if constexpr (!STRICT) primary_affine(prim, aff, lane, p.rot, p.focal, dmax);
+        }
         keep = tile_may_hit(prim, lane, dc, dmax);
       }
       const unsigned ballot = __ballot_sync(0xffffffffu, keep);
@@ -159,8 +225,10 @@ __device__ __forceinline__ void draw_fast_body(const FrameParams &p, const float
       const int i = base + threadIdx.x;
       bool keep = false;
       if (i < n) {
-        primary_constants(sc.g, prim, cam, i);
-        if constexpr (!STRICT) primary_affine(prim, aff, i, p.rot, p.focal, dmax);
+        if constexpr (!kHC) {
+          primary_constants(sc.g, prim, cam, i);
+          if constexpr (!STRICT) primary_affine(prim, aff, i, p.rot, p.focal, dmax);
+        }
         keep = tile_may_hit(prim, i, dc, dmax);
       }
       const unsigned ballot = __ballot_sync(0xffffffffu, keep);
@@ -180,7 +248,16 @@ __device__ __forceinline__ void draw_fast_body(const FrameParams &p, const float
   }
   __syncthreads();
   sc.n_prim = s_base;
+#if RT_SPH_RECT
+  // Can a primary ray of the tile reach a sphere?  The host projected the spheres (rt_api.cu: sphere_pixel_rect): a tile
+  // outside both pixel rectangles (which carry two pixels of margin) cannot.
+  bool spheres_visible = false;
+#pragma unroll
+  for (int i = 0; i < RT_SPHERES; i++)
+    spheres_visible |= tile_x < p.sph_px[i][2] && tile_x + kTW > p.sph_px[i][0] && tile_y < p.sph_px[i][3] && tile_y + kTH > p.sph_px[i][1];
+#else
   const bool spheres_visible = s_spheres_visible != 0;
+#endif
 #ifdef RT_DEBUG_PROLOGUE_ONLY  // experiment: cost of staging + binning alone
   if (in_frame) p.out[(size_t)y * p.W + x] = 0xff000000u | (unsigned)sc.n_prim;
   return;
@@ -279,6 +356,17 @@ __device__ __forceinline__ void draw_fast_body(const FrameParams &p, const float
           hs.point = (v0 + scale(SF(bu), e1)) + scale(SF(bv), e2);  // kernels.cl:124
           hs.normal = xyz<SF>(sc.g.tn[bi]);
           hs.color = sc.g.tcol[bi];
+#if RT_UV_AFFINE
+          if constexpr (!STRICT && kLazyPrimary) {
+            // Which rays take this exact path depends on the binned list, hence on the tile shape — so a triangle hit
+            // takes its hit point from the same affine (u, v) as the rays that were never in doubt: every lane mapping and
+            // every partition of the frame then produces the same bits.
+            const float vx = base.x.v + (float)cur_dx, vy = base.y.v + (float)cur_dy;
+            primary_uv(sc, bi, vx, vy, bu, bv);
+            const float4 A0 = sc.g.ta[bi], B0 = sc.g.tb[bi], C0 = sc.g.tc[bi];
+            hs.point = V3<SF>(SF(fmaf(bv, C0.x, fmaf(bu, B0.x, A0.x))), SF(fmaf(bv, C0.y, fmaf(bu, B0.y, A0.y))), SF(fmaf(bv, C0.z, fmaf(bu, B0.z, A0.z))));
+          }
+#endif
         }
         // the two spheres, strict as well (skipped when no ray of the block's tile can reach one)
         if (spheres_visible) closest_spheres<SF>(cam_s, dns, SF(bt), hs);
@@ -365,6 +453,14 @@ __device__ __forceinline__ void draw_fast_body(const FrameParams &p, const float
         hs.normal = V3<SF>(SF(hit.normal.x), SF(hit.normal.y), SF(hit.normal.z));
         hs.color = hit.color;
         bool bounced = false;
+        if constexpr (COOP) {
+          bounced = hs.id != -1 && hs.color.w <= 0.0f;
+          if (__ballot_sync(warp_mask, bounced) != 0u) resolve_bounces_coop<SF>(p, sc.g, warp_mask, hs, dir_s);
+          if (bounced) {
+            sc.clist = full_list;  // the warp list was built for the primary hits only
+            sc.n_clist = n_sh;
+          }
+        }
         while (hs.id != -1) {
           if (hs.color.w > 0.0f) {
             if (SINGLE && !have_jit) {
@@ -400,6 +496,15 @@ __device__ __forceinline__ void draw_fast_body(const FrameParams &p, const float
       } else {
       V3<float> dir(dir_s.x.v, dir_s.y.v, dir_s.z.v);
       float gain = 1.0f;
+      if constexpr (COOP) {
+        const bool specular = hit.id != -1 && hit.color.w <= 0.0f;
+        if (__ballot_sync(warp_mask, specular) != 0u) resolve_bounces_coop<float>(p, sc.g, warp_mask, hit, dir);
+        if (specular) {
+          gain = 0.9f;
+          sc.clist = full_list;  // the warp list was built for the primary hits only
+          sc.n_clist = n_sh;
+        }
+      }
       while (hit.id != -1) {
         if (hit.color.w > 0.0f) {
           if (SINGLE && !have_jit) {
@@ -427,11 +532,7 @@ __device__ __forceinline__ void draw_fast_body(const FrameParams &p, const float
         dir = ndir;
         hit.id = -1;
         hit.color.w = 1.0f;
-#ifdef RT_NO_BOUNCE_PLANES  // A/B switch: the plain loop over all triangles
-        closest_hit<float>(sc.g, start, dir, hit);
-#else
         closest_hit_bounce(sc.g, start, dir, hit);
-#endif
         gain = 0.9f;
         sc.clist = full_list;  // the warp list was built for the primary hits only
         sc.n_clist = n_sh;
@@ -460,12 +561,27 @@ __device__ __forceinline__ void draw_fast_body(const FrameParams &p, const float
   p.out[(size_t)y * p.W + x] = pack_argb<float>(V3<float>(total.x * ia, total.y * ia, total.z * ia));
 }
 
+// rt_signal_after_frame: every block makes its stores visible system-wide before it counts itself done; the block that
+// sees the count complete has all of them behind it, tells the owner of the frame and re-arms the counter.
+__device__ __forceinline__ void block_done(const FrameParams &p) {
+  if (!p.signal_flag) return;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence_system();
+    if (atomicAdd(p.work_counter + 1, 1u) == gridDim.x - 1) {
+      p.work_counter[1] = 0u;
+      __threadfence_system();
+      asm volatile("red.release.sys.global.add.u32 [%0], 1;" ::"l"(p.signal_flag) : "memory");
+    }
+  }
+}
+
 template <int CH, bool SINGLE, bool STRICT, bool SPLIT>
-__global__ void __launch_bounds__(kThreads, STRICT ? RT_STRICT_MINBLOCKS : RT_MINBLOCKS) draw_fast_kernel(const __grid_constant__ FrameParams p,
-                                                                           const float4 *__restrict__ scene, int n, int n_sh) {
+__global__ void __launch_bounds__(kThreads, STRICT ? RT_STRICT_MINBLOCKS : RT_MINBLOCKS)
+    draw_fast_kernel(const __grid_constant__ FrameParams p, const float4 *__restrict__ scene, const float4 *__restrict__ fconst, int n, int n_sh) {
   int bx, by;
   tile_of_block<SPLIT, false>(p, (int)blockIdx.x, bx, by);
-  draw_fast_body<CH, SINGLE, STRICT, SPLIT>(p, scene, n, n_sh, bx, by);
+  draw_fast_body<CH, SINGLE, STRICT, SPLIT, SPLIT>(p, scene, fconst, n, n_sh, bx, by);
 }
 
 // Mixed launch for shares of a frame that cannot fill the GPU: tiles inside the screen rectangle of a sphere (mirror / glass
@@ -474,20 +590,38 @@ __global__ void __launch_bounds__(kThreads, STRICT ? RT_STRICT_MINBLOCKS : RT_MI
 // arguments (rt_api.cu: sphere_rects) — nothing is built, cached or copied per camera; they only steer performance: either
 // mapping renders any tile correctly.
 template <int CH, bool SINGLE, bool STRICT>
-__global__ void __launch_bounds__(kThreads, STRICT ? RT_STRICT_MINBLOCKS : RT_MINBLOCKS) draw_fast_mixed_kernel(const __grid_constant__ FrameParams p,
-                                                                                 const float4 *__restrict__ scene, int n, int n_sh) {
+__global__ void __launch_bounds__(kThreads, STRICT ? RT_STRICT_MINBLOCKS : RT_MINBLOCKS)
+    draw_fast_mixed_kernel(const __grid_constant__ FrameParams p, const float4 *__restrict__ scene, const float4 *__restrict__ fconst, int n, int n_sh) {
   int bx, by;
   if ((int)blockIdx.x < p.n_split) {
-    if (!tile_of_block<true, true>(p, (int)blockIdx.x, bx, by)) return;
-    draw_fast_body<CH, SINGLE, STRICT, true>(p, scene, n, n_sh, bx, by);
+    if (tile_of_block<true, true>(p, (int)blockIdx.x, bx, by)) draw_fast_body<CH, SINGLE, STRICT, true, true>(p, scene, fconst, n, n_sh, bx, by);
   } else {
-    if (!tile_of_block<false, true>(p, (int)blockIdx.x - p.n_split, bx, by)) return;
-    draw_fast_body<CH, SINGLE, STRICT, false>(p, scene, n, n_sh, bx, by);
+    if (tile_of_block<false, true>(p, (int)blockIdx.x - p.n_split, bx, by)) draw_fast_body<CH, SINGLE, STRICT, false, true>(p, scene, fconst, n, n_sh, bx, by);
   }
+  block_done(p);
 }
 
 #define RT_CAT2(a, b) a##b
 #define RT_CAT(a, b) RT_CAT2(a, b)
+
+// One block per tile; `blocks` of them.
+template <class K>
+static cudaError_t launch_tiles(K kern, rt_ctx *ctx, FrameParams &fp, int blocks, cudaStream_t stream, size_t extra_smem, const char *name) {
+  const size_t smem = brute_smem_bytes(ctx->n, ctx->n_sh) + extra_smem;
+  if (smem > 32 * 1024) {  // dynamic + the kernels' static shared memory (kDrawStaticSmem) must stay under the 48 KB default
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+  }
+  ctx->last_kernel = name;
+  if (blocks <= 0) {
+    if (fp.signal_flag) return launch_peer_add(fp.signal_flag, stream);  // nothing to draw: the delivery still has to be reported
+    return cudaSuccess;
+  }
+  fp.work_counter = ctx->d_work + 2 * (ctx->work_seq++ % rt_ctx::kWorkSlots);
+  kern<<<blocks, kThreads, smem, stream>>>(fp, ctx->d_scene, ctx->d_fconst, ctx->n, ctx->n_sh);
+  ctx->launches++;
+  return cudaGetLastError();
+}
 
 cudaError_t RT_CAT(launch_fast_ch, RT_FAST_CH)(rt_ctx *ctx, const FrameParams &fp_in, cudaStream_t stream) {
   constexpr int CH = RT_FAST_CH;
@@ -497,25 +631,49 @@ cudaError_t RT_CAT(launch_fast_ch, RT_FAST_CH)(rt_ctx *ctx, const FrameParams &f
   SplitMode mode = split_mode(ctx, fp);
   int n_sub = 0;
   if (mode == kSplitHeavy && (n_sub = sphere_rects(fp)) == 0) mode = kSplitNone;  // no sphere in sight: nothing to split
+  if (mode != kSplitHeavy) fp.n_rect = 0;
+  // this rank's share of the tiles (multi-GPU block interleave)
+  const int tw = mode == kSplitAll ? kSplitTileW : kTileW, th = mode == kSplitAll ? kSplitTileH : kTileH;
+  fp.grid_x = (fp.W + tw - 1) / tw;
+  fp.n_blocks = fp.grid_x * ((fp.rows + th - 1) / th);
+  fp.blk_stride = ctx->cfg.block_stride > 1 ? ctx->cfg.block_stride : 1;
+  fp.blk_phase = ctx->cfg.block_stride > 1 ? ctx->cfg.block_phase : 0;
+  fp.tile_order = tile_order_for(ctx, fp.row0, fp.rows, fp.grid_x, fp.n_blocks, tw, th);
+  const int my_tiles = fp.n_blocks > fp.blk_phase ? (fp.n_blocks - fp.blk_phase + fp.blk_stride - 1) / fp.blk_stride : 0;
+  const int my_split = n_sub > fp.blk_phase ? (n_sub - fp.blk_phase + fp.blk_stride - 1) / fp.blk_stride : 0;
+  fp.n_split = my_split;
+  fp.n_split_items = my_split;
+  fp.n_items = my_tiles + my_split;
   char name[96];
-  snprintf(name, sizeof name, "%s<%d,%s,%s%s>", mode == kSplitHeavy ? "draw_fast_mixed_kernel" : "draw_fast_kernel", CH, single ? "true" : "false",
-           strict ? "true" : "false", mode == kSplitHeavy ? "" : (mode == kSplitAll ? ",true" : ",false"));
+  snprintf(name, sizeof name, "draw_fast_kernel<%d,%s,%s,%s>", CH, single ? "true" : "false", strict ? "true" : "false",
+           mode == kSplitHeavy ? "mixed" : (mode == kSplitAll ? "split" : "plain"));
+  // rt_signal_after_frame: the mixed kernel (what a share of a frame on several GPUs runs) reports the delivery itself, from
+  // its last block; behind the other kernels a one-thread kernel does (an exit path through a block-wide barrier costs the
+  // plain kernel 48 bytes of stack it does not have)
+  uint32_t *signal_behind = nullptr;
+  if (mode != kSplitHeavy && fp.signal_flag) {
+    signal_behind = fp.signal_flag;
+    fp.signal_flag = nullptr;
+  }
+  auto finish = [&](cudaError_t e) {
+    if (e == cudaSuccess && signal_behind) {
+      e = launch_peer_add(signal_behind, stream);
+      ctx->launches++;
+    }
+    return e;
+  };
+#define RT_LAUNCH(K_) finish(launch_tiles(K_, ctx, fp, fp.n_items, stream, extra, name))
   if (mode == kSplitHeavy) {
-    if (strict) return single ? launch_kernel_mixed(draw_fast_mixed_kernel<CH, true, true>, ctx, fp, stream, n_sub, extra, name)
-                              : launch_kernel_mixed(draw_fast_mixed_kernel<CH, false, true>, ctx, fp, stream, n_sub, extra, name);
-    return single ? launch_kernel_mixed(draw_fast_mixed_kernel<CH, true, false>, ctx, fp, stream, n_sub, extra, name)
-                  : launch_kernel_mixed(draw_fast_mixed_kernel<CH, false, false>, ctx, fp, stream, n_sub, extra, name);
+    if (strict) return single ? RT_LAUNCH((draw_fast_mixed_kernel<CH, true, true>)) : RT_LAUNCH((draw_fast_mixed_kernel<CH, false, true>));
+    return single ? RT_LAUNCH((draw_fast_mixed_kernel<CH, true, false>)) : RT_LAUNCH((draw_fast_mixed_kernel<CH, false, false>));
   }
   if (mode == kSplitAll) {
-    if (strict) return single ? launch_kernel(draw_fast_kernel<CH, true, true, true>, ctx, fp, stream, extra, name, kSplitTileW, kSplitTileH)
-                              : launch_kernel(draw_fast_kernel<CH, false, true, true>, ctx, fp, stream, extra, name, kSplitTileW, kSplitTileH);
-    return single ? launch_kernel(draw_fast_kernel<CH, true, false, true>, ctx, fp, stream, extra, name, kSplitTileW, kSplitTileH)
-                  : launch_kernel(draw_fast_kernel<CH, false, false, true>, ctx, fp, stream, extra, name, kSplitTileW, kSplitTileH);
+    if (strict) return single ? RT_LAUNCH((draw_fast_kernel<CH, true, true, true>)) : RT_LAUNCH((draw_fast_kernel<CH, false, true, true>));
+    return single ? RT_LAUNCH((draw_fast_kernel<CH, true, false, true>)) : RT_LAUNCH((draw_fast_kernel<CH, false, false, true>));
   }
-  if (strict) return single ? launch_kernel(draw_fast_kernel<CH, true, true, false>, ctx, fp, stream, extra, name)
-                            : launch_kernel(draw_fast_kernel<CH, false, true, false>, ctx, fp, stream, extra, name);
-  return single ? launch_kernel(draw_fast_kernel<CH, true, false, false>, ctx, fp, stream, extra, name)
-                : launch_kernel(draw_fast_kernel<CH, false, false, false>, ctx, fp, stream, extra, name);
+  if (strict) return single ? RT_LAUNCH((draw_fast_kernel<CH, true, true, false>)) : RT_LAUNCH((draw_fast_kernel<CH, false, true, false>));
+  return single ? RT_LAUNCH((draw_fast_kernel<CH, true, false, false>)) : RT_LAUNCH((draw_fast_kernel<CH, false, false, false>));
+#undef RT_LAUNCH
 }
 
 }  // namespace rt

@@ -243,6 +243,20 @@ __device__ __forceinline__ bool primary_fast(const FastScene &sc, float vx, floa
   return sure;
 }
 
+// (u, v) of the ray through (vx, vy) on triangle i, by the affine forms and approximate division — the values primary_fast
+// returns for a hit, for a winner that the exact path had to decide.
+__device__ __forceinline__ void primary_uv(const FastScene &sc, int i, float vx, float vy, float &bu, float &bv) {
+  const float4 *q = sc.aff + 3 * i;
+  const float4 QA = q[0], QB = q[1], QC = q[2];
+  const float dn = fmaf(vx, QA.x, fmaf(vy, QA.y, QA.z));
+  const float E1 = fmaf(vx, QB.x, fmaf(vy, QB.y, QB.z));
+  const float E2 = fmaf(vx, QC.x, fmaf(vy, QC.y, QC.z));
+  const unsigned sb = __float_as_uint(dn) & 0x80000000u;
+  const float inv = rcp_approx(fabsf(dn));
+  bu = xor_sign(E1, sb) * inv;
+  bv = xor_sign(E2, sb) * inv;
+}
+
 // Does the ray cam + x d0 surely miss both spheres?  (disc/4 = (d0.L)^2 - (d0.d0)(L.L - r^2) < 0 with a relative margin;
 // kernels.cl:132-163.)  Anything else — a hit, a graze, the camera inside a sphere — goes to the exact sequence.
 __device__ __forceinline__ bool spheres_surely_missed(V3<float> d0, V3<float> cam) {
@@ -293,7 +307,122 @@ __device__ __forceinline__ void primary_triangles(const FastScene &sc, V3<float>
   }
 }
 
-// Closest hit of a bounce ray, fast policy (kernels.cl:168-241).  Same decisions as closest_tri_test<float> — the inside
+// ---------------------------------------------------------------------------------------------
+// Closest hit of a bounce ray (kernels.cl:168-241), in two steps: the triangle search fills a ClosestState, then
+// finish_closest turns the winner into a hit record and continues with the two spheres.  The search comes in a
+// lane-parallel form (every lane scans the triangles for its own ray) and a warp-cooperative form (the lanes of a warp
+// share out the triangles of ONE ray at a time) — same per-triangle arithmetic, same winner, hence the same bits.
+// ---------------------------------------------------------------------------------------------
+
+// One candidate of the fast policy: (t, u, v) of triangle i for the ray (start, dir), or false.  The inside test runs on
+// sign-corrected triple products, t = ts / |dn|.  Two plane tests that cost one 16-byte load and six FMAs come first:
+//   dn = d.N, bn = (o - v0).N = o.N - v0.N:   t = -bn/dn < 0 (the plane lies behind the ray)  -> no candidate
+//   |bn| > t_limit |dn| (the plane is crossed beyond t_limit, with a relative margin far above rounding) -> no candidate
+// (t_limit = the current best of a sequential scan, which would reject the candidate anyway; RT_MAXFLOAT = no limit).
+__device__ __forceinline__ bool bounce_candidate(const SceneView &sc, int i, V3<float> start, V3<float> dir, float t_limit, float &t, float &u,
+                                                 float &v) {
+  const float4 P = sc.tnd[i];
+  const float dn = fmaf(dir.x, P.x, fmaf(dir.y, P.y, dir.z * P.z));
+  const float bn = fmaf(start.x, P.x, fmaf(start.y, P.y, fmaf(start.z, P.z, -P.w)));
+  const unsigned sb = __float_as_uint(dn) & 0x80000000u;
+  const float ts = xor_sign(-bn, sb), adn = fabsf(dn);
+  if (!(ts >= 0.0f) || ts > t_limit * adn * 1.0001f) return false;  // (NaN rays fail the first test, as they fail the full one)
+  const float4 A = sc.ta[i], Bq = sc.tb[i], C = sc.tc[i];
+  const V3<float> b(start.x - A.x, start.y - A.y, start.z - A.z), e1(Bq.x, Bq.y, Bq.z), e2(C.x, C.y, C.z);
+  const V3<float> q(b.y * dir.z - b.z * dir.y, b.z * dir.x - b.x * dir.z, b.x * dir.y - b.y * dir.x);
+  const float us = xor_sign(-dot(e2, q), sb), vs = xor_sign(dot(e1, q), sb);
+  if (!((us >= 0.0f) & (vs >= 0.0f) & ((us + vs) <= adn))) return false;
+  const float inv = __frcp_rn(adn);
+  t = ts * inv;
+  u = us * inv;
+  v = vs * inv;
+  return true;
+}
+
+// Lane-parallel search.  Fast policy: a bounce ray inside the box faces about half the planes and, once it has a hit, most
+// of the rest lie behind it; the rays of a warp leave neighbouring points of a sphere, so they mostly agree and only the
+// survivors of the plane tests load the vertices.  Strict policy: the reference's loop.
+__device__ __forceinline__ void closest_triangles(const SceneView &sc, V3<float> start, V3<float> dir, ClosestState<float> &cs) {
+  for (int i = 0; i < sc.n; i++) {
+    float t, u, v;
+    if (bounce_candidate(sc, i, start, dir, cs.t, t, u, v) && t < cs.t) {  // strict '<', ascending index: lowest index wins a tie
+      cs.id = i;
+      cs.t = t;
+      cs.u = u;
+      cs.v = v;
+    }
+  }
+}
+__device__ __forceinline__ void closest_triangles(const SceneView &sc, V3<sfloat> start, V3<sfloat> dir, ClosestState<sfloat> &cs) {
+  const V3<sfloat> nd = -dir;
+  for (int i = 0; i < sc.n; i++) closest_tri_test<sfloat, true>(sc.ta[i], sc.tb[i], sc.tc[i], start, nd, i, i, cs);
+}
+
+// Warp-cooperative search — ray compaction across bounces: after the first bounces only a few lanes of a warp still hold
+// a live mirror / glass ray (`rays`: their ballot), and a lane scanning all triangles alone is the serial chain a small
+// launch ends up waiting for.  So the live rays are taken one at a time: the owner broadcasts origin and direction
+// (shuffles), every lane of the warp tests ITS share of the triangles with the same arithmetic as the lane-parallel
+// search, and two integer REDUX reductions pick the winner — smallest t (a non-negative float orders like its bits),
+// then smallest triangle index among equal t, which is the reference's "strict <, ascending index" rule (kernels.cl:120).
+// (u, v, t) travel back to the owner by shuffle.  All lanes of warp_mask must call this together.
+template <class T>
+__device__ __forceinline__ void closest_triangles_coop(const SceneView &sc, unsigned warp_mask, unsigned rays, V3<T> start, V3<T> dir,
+                                                       ClosestState<T> &cs) {
+  const int lane = threadIdx.x & 31;
+  const int n_act = __popc(warp_mask), rank = __popc(warp_mask & ((1u << lane) - 1u));
+  while (rays) {
+    const int s = __ffs(rays) - 1;
+    rays &= rays - 1u;
+    const V3<T> o(T(__shfl_sync(warp_mask, raw(start.x), s)), T(__shfl_sync(warp_mask, raw(start.y), s)), T(__shfl_sync(warp_mask, raw(start.z), s)));
+    const V3<T> d(T(__shfl_sync(warp_mask, raw(dir.x), s)), T(__shfl_sync(warp_mask, raw(dir.y), s)), T(__shfl_sync(warp_mask, raw(dir.z), s)));
+    ClosestState<T> my;
+    my.reset();
+    if constexpr (is_strict<T>::value) {
+      const V3<T> nd = -d;
+      for (int i = rank; i < sc.n; i += n_act) closest_tri_test<T, true>(sc.ta[i], sc.tb[i], sc.tc[i], o, nd, i, i, my);
+    } else {
+      for (int i = rank; i < sc.n; i += n_act) {
+        float t, u, v;
+        if (bounce_candidate(sc, i, o, d, RT_MAXFLOAT, t, u, v) && t < my.t) {
+          my.id = i;
+          my.t = t;
+          my.u = u;
+          my.v = v;
+        }
+      }
+    }
+    // a candidate has 0 <= t < MAXFLOAT (never NaN); -0 orders with +0
+    const unsigned key = (my.id < 0) ? 0xffffffffu : ((raw(my.t) == 0.0f) ? 0u : __float_as_uint(raw(my.t)));
+    const unsigned kmin = __reduce_min_sync(warp_mask, key);
+    if (kmin == 0xffffffffu) continue;  // no triangle hit (warp-uniform)
+    const unsigned idk = (key == kmin) ? (unsigned)my.id : 0xffffffffu;
+    const unsigned imin = __reduce_min_sync(warp_mask, idk);
+    const int w = __ffs(__ballot_sync(warp_mask, idk == imin)) - 1;
+    const float wt = __shfl_sync(warp_mask, raw(my.t), w), wu = __shfl_sync(warp_mask, raw(my.u), w), wv = __shfl_sync(warp_mask, raw(my.v), w);
+    if (lane == s) {
+      cs.id = (int)imin;
+      cs.slot = (int)imin;
+      cs.t = T(wt);
+      cs.u = T(wu);
+      cs.v = T(wv);
+    }
+  }
+}
+
+// The winner's hit record, then the two spheres (kernels.cl:124-127, :132-163)
+template <class T>
+__device__ __forceinline__ void finish_closest(const SceneView &sc, V3<T> start, V3<T> dir, const ClosestState<T> &cs, HitRec<T> &hit) {
+  if (cs.id >= 0) {
+    hit.id = cs.id;
+    hit.point = hit_point<T>(sc.ta[cs.id], sc.tb[cs.id], sc.tc[cs.id], cs.u, cs.v);
+    hit.normal = xyz<T>(sc.tn[cs.id]);
+    hit.color = sc.tcol[cs.id];
+  }
+  closest_spheres<T>(start, dir, cs.t, hit);
+}
+
+// Closest hit of a bounce ray, fast policy (kernels.cl:168-241), lane-parallel, in one piece (the form the full-size
+// launches use: it compiles to fewer live registers than closest_triangles + finish_closest).  Same decisions as closest_tri_test<float> — the inside
 // test on sign-corrected triple products, t = ts / |dn| compared with strict '<' in ascending index order — behind two
 // plane tests that cost one 16-byte load and six FMAs per triangle:  dn = d.N, bn = (o - v0).N = o.N - v0.N,
 //   t = -bn/dn < 0        (the plane lies behind the ray)              -> skip
@@ -348,10 +477,11 @@ template <int CH> struct Jitters {  // in registers
 // float2 slot (c*CH/2 + k/2)*STRIDE + thread holds (j_c[k], j_c[k+1]) — so one LDS.64 feeds one packed fma.rn.f32x2
 // (two samples per issue slot, rt_fast.cuh: shadow_lit_count).  Odd CH: one float per slot, (3k + c)*STRIDE + thread.
 template <int CH, int STRIDE> struct JittersShared {
-#ifdef RT_NO_F32X2  // A/B switch: scalar per-sample tests
-  static constexpr bool kPacked = false;
-#else
+#ifdef RT_F32X2  // A/B switch (measured: no gain on B200 — the per-sample loop is 4 % of the instructions — and the thirteen
+                 // duplicated operand pairs cost registers the kernel does not have)
   static constexpr bool kPacked = (CH % 2) == 0;
+#else
+  static constexpr bool kPacked = false;
 #endif
   float *p;  // this thread's column: base + thread (odd CH) or base + 2*thread (even CH)
   __device__ __forceinline__ static float *column(float *base, int thread) { return base + (kPacked ? 2 * thread : thread); }

@@ -39,6 +39,18 @@ struct rt_ctx {
   // then 4 float4 per shadow caster and n_sh bounding spheres (fast kernel, rt_fast.cuh)
   float4 *d_scene = nullptr;
   int n = 0, n_sh = 0;
+  // Per-frame triangle constants of the tuned kernels (6n float4: the exact primary test's constants, then their affine
+  // form — rt_fast.cuh), computed on the host whenever the camera changes and copied in stream order in front of the launch
+  float4 *d_fconst = nullptr;
+  std::vector<float4> h_tri;     // ta | tb | tc of the uploaded scene (host copy the constants are computed from)
+  std::vector<float4> h_fconst;
+  float fconst_key[14] = {0};
+  bool fconst_valid = false;
+  cudaStream_t fconst_stream = nullptr;  // the stream the current constants were copied on
+  // work counters of the persistent launches: a ring, so that launches in flight on different streams never share one
+  static constexpr int kWorkSlots = 64;
+  unsigned *d_work = nullptr;
+  unsigned long long work_seq = 0;
   bool have_scene = false;
   bool use_bvh = false;
   void *bvh_view = nullptr;         // rt::BvhView (rt_bvh.cu)
@@ -46,9 +58,11 @@ struct rt_ctx {
   int sm_count = 0;
   uint64_t launches = 0;
   unsigned long long *d_ray_counters = nullptr;  // RT_FLAG_COUNT_RAYS
+  uint32_t *signal_flag = nullptr;               // rt_signal_after_frame: applies to the next draw launch, then cleared
   const uint32_t *gate_flag = nullptr;           // rt_gate_next_frame: applies to the next draw launch, then cleared
   uint32_t gate_value = 0;
-  const uint32_t *gate_flag_cached = nullptr;    // the flag d_gate_seen mirrors
+  const uint32_t *gate_flag_cached[2] = {nullptr, nullptr};  // the flags d_gate_seen[0..1] mirror
+  unsigned gate_victim = 0;
   uint32_t *d_gate_seen = nullptr;
   int *d_wait_status = nullptr;                  // set by a rt_peer_wait kernel that timed out
   bool peer_waits = false;
@@ -72,6 +86,7 @@ size_t fast_extra_smem(int S);
 constexpr size_t kDrawStaticSmem = 6144;  // the mixed kernel carries the statics of both lane mappings (5.2 KB)
 // rt_peak.cu (small utility kernels)
 cudaError_t launch_peer_signal(uint32_t *flag, uint32_t value, cudaStream_t stream);
+cudaError_t launch_peer_add(uint32_t *counter, cudaStream_t stream);
 cudaError_t launch_peer_wait(const uint32_t *flags, int n, uint32_t value, int *status, cudaStream_t stream);
 // rt_bvh.cu
 cudaError_t bvh_build(rt_ctx *ctx, const float *verts, const float *normals, const float *colors, int n);

@@ -17,6 +17,10 @@ namespace rt {
 #define RT_STRICT_MINBLOCKS 2
 #endif
 constexpr int kThreads = RT_THREADS, kTileW = 16, kTileH = kThreads / 16;
+#ifndef RT_FAST_THREADS  // block size of the tuned kernels (rt_draw_fast.cu): their warps are independent workers
+#define RT_FAST_THREADS 256
+#endif
+constexpr int kFastThreads = RT_FAST_THREADS;
 // SPLIT launches (four lanes per pixel, see rt_draw_fast.cu): a block covers 8 x 8 pixels, a warp 4 x 2
 constexpr int kSplitTileW = 8, kSplitTileH = kThreads / 4 / 8;
 
@@ -105,12 +109,15 @@ void visible_rect(const rt_ctx *ctx, FrameParams &fp);
 // rt_api.cu: how should this launch map lanes to pixels? (flags, AA grid, size of the launch)
 enum SplitMode { kSplitNone = 0, kSplitAll = 1, kSplitHeavy = 2 };
 SplitMode split_mode(const rt_ctx *ctx, const FrameParams &fp);
+// rt_api.cu: per-frame host work of the tuned kernels — triangle constants for this camera into ctx->d_fconst (copied on
+// `stream` when the camera changed), fp.dmax, fp.sph_px.  Call once per frame, in front of the launch(es).
+cudaError_t prepare_frame(rt_ctx *ctx, FrameParams &fp, cudaStream_t stream);
 // rt_api.cu: the sphere rectangles of a mixed launch for this camera and row range (fills fp.n_rect, fp.rect, fp.rect_first);
 // returns the number of 8x8 sub-tiles they hold.  Pure host arithmetic per launch: nothing is cached, copied or synchronised.
 int sphere_rects(FrameParams &fp);
 
 // float4 slots of the scene part of the fast kernel's shared memory (see brute_smem_bytes)
-__host__ __device__ inline int scene_smem_float4(int n, int n_sh) { return 12 * n + 5 * n_sh + (n + n_sh + 3) / 4 + 1; }
+__host__ __device__ inline int scene_smem_float4(int n, int n_sh) { return 12 * n + 5 * n_sh + ((kFastThreads / 32) * n + n_sh + 3) / 4 + 1; }
 
 // extra_smem: dynamic shared memory beyond the scene (fast kernels: fast_extra_smem); name: what rt_last_kernel_name reports
 template <class K>

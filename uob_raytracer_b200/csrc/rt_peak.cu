@@ -48,6 +48,16 @@ __global__ void peer_wait_kernel(const uint32_t *flags, int n, uint32_t value, i
   __threadfence_system();
 }
 
+__global__ void peer_add_kernel(uint32_t *counter) {
+  __threadfence_system();
+  asm volatile("red.release.sys.global.add.u32 [%0], 1;" ::"l"(counter) : "memory");
+}
+
+cudaError_t launch_peer_add(uint32_t *counter, cudaStream_t stream) {
+  peer_add_kernel<<<1, 1, 0, stream>>>(counter);
+  return cudaGetLastError();
+}
+
 cudaError_t launch_peer_signal(uint32_t *flag, uint32_t value, cudaStream_t stream) {
   peer_signal_kernel<<<1, 1, 0, stream>>>(flag, value);
   return cudaGetLastError();

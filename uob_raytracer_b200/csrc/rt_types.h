@@ -24,6 +24,16 @@ struct FrameParams {
   int n_split, n_rect;
   int rect[2][4];
   int rect_first[2];
+  // persistent launches of the tuned kernels (rt_draw_fast.cu): blocks take tiles from work_counter[0] until n_items are
+  // handed out (n_split_items = n_split of them are the four-lanes-per-pixel sub-tiles of a mixed launch and come first).
+  // work_counter[1] counts finished blocks: the last one re-arms both words.
+  int n_items, n_split_items;
+  unsigned *work_counter;
+  // per-frame camera data computed on the host (rt_api.cu: prepare_frame): the longest un-normalised primary ray direction
+  // of the frame (x 1.001), and the pixel rectangle {x0, y0, x1, y1} (half-open, two pixels of margin) that contains every
+  // primary ray able to reach sphere i — empty if none can, the whole frame if the projection is not bounded
+  float dmax;
+  int sph_px[2][4];
   // pixel rectangle [vis_x0, vis_x1) x [vis_y0, vis_y1) outside which no primary ray can hit anything (projection of the
   // scene's bounding box, rt_api.cu): tiles outside it are black without looking at the scene
   int vis_x0, vis_y0, vis_x1, vis_y1;
@@ -31,6 +41,9 @@ struct FrameParams {
   // the previous frame" flag).  gate_seen is a device-local copy of the last value observed, gate_status the time-out flag.
   const uint32_t *gate_flag;
   uint32_t gate_value;
+  // rt_signal_after_frame: when the last block of this launch is done and every pixel it stored is visible system-wide,
+  // *signal_flag += 1 (a counter in the frame owner's memory: "one more rank has delivered this frame")
+  uint32_t *signal_flag;
   uint32_t *gate_seen;
   int *gate_status;
   int A, S, B;     // AA edge, shadow samples, max bounces

@@ -170,6 +170,30 @@ class Renderer:
         """The next render_device stores no pixel before *flag_ptr >= value (the wait folded into the draw kernel)."""
         self._check(self._lib.rt_gate_next_frame(self._ctx, flag_ptr, value))
 
+    @property
+    def frame_slot_bytes(self) -> int:
+        """Distance in bytes between the two frame slots of this context (pixels + hand-over flags)."""
+        return 4 * int(self._lib.rt_frame_slot_words(self._ctx))
+
+    def signal_after_frame(self, counter_ptr: int) -> None:
+        """The next render_device ends with *counter_ptr += 1 once all its pixels are visible system-wide (no extra launch)."""
+        self._check(self._lib.rt_signal_after_frame(self._ctx, counter_ptr))
+
+    def stream_wait_geq(self, word_ptr: int, value: int, stream: int = 0) -> None:
+        self._check(self._lib.rt_stream_wait_geq(self._ctx, word_ptr, value, stream or None))
+
+    def stream_write(self, word_ptr: int, value: int, stream: int = 0) -> None:
+        self._check(self._lib.rt_stream_write(self._ctx, word_ptr, value, stream or None))
+
+    def read_frame_slot(self, slot: int, out: np.ndarray | None = None) -> np.ndarray:
+        if out is None:
+            out = np.empty((self.height, self.width), np.uint32)
+        self._check(self._lib.rt_read_frame_slot(self._ctx, slot, out.ctypes.data))
+        return out
+
+    def read_frame_slot_host_ptr(self, slot: int, host_ptr: int) -> None:
+        self._check(self._lib.rt_read_frame_slot(self._ctx, slot, host_ptr))
+
     def set_stream(self, stream: int) -> None:
         """Use the caller's cudaStream_t (0 = back to the context's own) for everything that follows."""
         self._check(self._lib.rt_set_stream(self._ctx, stream or None))
