@@ -229,6 +229,20 @@ int rt_stream_wait_geq(rt_ctx *ctx, const uint32_t *dev_word, uint32_t value, vo
 int rt_stream_write(rt_ctx *ctx, uint32_t *dev_word, uint32_t value, void *stream);
 int rt_read_frame_slot(rt_ctx *ctx, int slot, uint32_t *host_argb);
 
+/* Parallel egress.  The reference reads the frame back over one link (skeleton.cpp:179); with N GPUs behind N PCIe links
+ * the frame can leave the GPUs N times faster if every GPU holds the rows it will copy.  rt_set_strip_targets deals the
+ * rows out in strips of strip_rows rows (a multiple of 16): from now on the draw kernels of this context store row y into
+ * dev_frames[(y / strip_rows) % n] — the whole-frame buffer of the strip's owner, its own or a peer's (mapped with
+ * rt_ipc_open_frame; the stores cross NVLink) — whatever partition of the pixels the context renders.  Every GPU then
+ * ends up with strips phase, phase + n, ... of the complete frame and rt_read_strips copies exactly those into the same
+ * rows of a host frame (asynchronously; a 2-D copy).  With the host frame in memory that all ranks' processes share and
+ * have registered (rt_host_register on a shared mapping), the N copies run side by side.  n <= 1 switches it off.
+ * Tuned brute-force kernels only. */
+int rt_set_strip_targets(rt_ctx *ctx, uint32_t *const *dev_frames, int n, int strip_rows);
+int rt_read_strips(rt_ctx *ctx, int slot, int strip_rows, int n, int phase, uint32_t *host_argb, void *stream);
+int rt_host_register(void *p, size_t bytes);
+int rt_host_unregister(void *p);
+
 /* Host-side launch planning, exposed for the CPU test suite (pure functions: no context, no device).  No reference
  * counterpart — the reference launches one work-item per pixel over the whole frame (skeleton.cpp:170-172).
  * rt_debug_visible_rect: the pixel rectangle {x0, y0, x1, y1} (half-open) outside which no primary ray of this camera

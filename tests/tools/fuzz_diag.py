@@ -23,7 +23,7 @@ golden = (z["verts"], z["normals"], z["colors"])
 def case(seed):
     """Same draw sequence as test_fuzz_culled_strict_equals_reference_loops."""
     rng = np.random.default_rng(77000 + seed)
-    v, nn, c, n_extra = T._fuzz_scene(rng, golden)
+    v, nn, c, n_extra, coplanar = T._fuzz_scene(rng, golden)
     W, H = int(rng.integers(33, 130)), int(rng.integers(20, 90))
     A = int(rng.choice([1, 2, 2, 3, 4]))
     S = int(rng.choice([1, 2, 4, 5, 8, 10, 3]))
@@ -60,7 +60,7 @@ def case(seed):
     span = float(rng.choice([0.3, 0.8, np.pi / 2]))
     m = dict(W=W, H=H, aa=A, shadow_samples=S, max_bounces=B, focal=f, cam=cam, light=light,
              yaw=float(rng.uniform(-span, span)), pitch=float(rng.uniform(-span, span)))
-    return m, u.Scene(v, nn, c), n_extra, where, lw
+    return m, u.Scene(v, nn, c), n_extra, where, (lw, coplanar)
 
 
 def report(seed, verbose=True):
@@ -71,7 +71,7 @@ def report(seed, verbose=True):
     m0 = dict(m, max_bounces=0)
     bounce_px = T._render(m0, scene, True, split_pixels=False) != strict
     off1, off16 = d > 1, d > 16
-    line = (f"seed {seed:3d} {m['W']:3d}x{m['H']:2d} aa{m['aa']} S{m['shadow_samples']:2d} B{m['max_bounces']:2d} +{n_extra:2d} cam{where} light{lw}: "
+    line = (f"seed {seed:3d} {m['W']:3d}x{m['H']:2d} aa{m['aa']} S{m['shadow_samples']:2d} B{m['max_bounces']:2d} +{n_extra:2d} cam{where} light{lw[0]} coplanar={int(lw[1])}: "
             f"within1 {100 * (1 - off1.mean()):7.3f}%  >1: {int(off1.sum()):4d} (bounce px {int((off1 & bounce_px).sum()):4d}, direct {int((off1 & ~bounce_px).sum()):4d})  "
             f">16: {int(off16.sum()):4d} (bounce {int((off16 & bounce_px).sum()):4d})  bounce px share {100 * bounce_px.mean():5.1f}%")
     if verbose:

@@ -75,6 +75,10 @@ RT_SYMBOLS = {
     "rt_stream_wait_geq": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_uint32, ctypes.c_void_p]),
     "rt_stream_write": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_uint32, ctypes.c_void_p]),
     "rt_read_frame_slot": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p]),
+    "rt_set_strip_targets": (ctypes.c_int, [ctypes.c_void_p, ctypes.POINTER(ctypes.c_void_p), ctypes.c_int, ctypes.c_int]),
+    "rt_read_strips": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p]),
+    "rt_host_register": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_size_t]),
+    "rt_host_unregister": (ctypes.c_int, [ctypes.c_void_p]),
     "rt_debug_visible_rect": (ctypes.c_int, [ctypes.c_void_p, c_float_p, c_float_p, c_float_p, c_float_p, ctypes.c_float,
                                              ctypes.POINTER(ctypes.c_int)]),
     "rt_debug_tile_lists": (ctypes.c_int, [ctypes.c_void_p, c_float_p, c_float_p, ctypes.c_float, ctypes.POINTER(ctypes.c_int), ctypes.c_int,

@@ -674,6 +674,17 @@ static int render_impl(rt_ctx *ctx, const float rot12[12], const float cam[4], c
     signal_after = nullptr;
   }
   fp.out = dev_argb ? dev_argb : ctx->d_frame;
+  fp.n_out = 0;
+  fp.strip_rows = 1;
+  if (ctx->n_strip_targets > 1) {
+    if (ctx->use_bvh || ctx->d_ray_counters || ((ctx->cfg.flags & RT_FLAG_STRICT_IEEE) && (ctx->cfg.flags & RT_FLAG_REFERENCE_LOOPS))) {
+      ctx->err = "rt_set_strip_targets: only the tuned brute-force kernels deal rows out over several frame buffers";
+      return RT_ERR_INVALID;
+    }
+    fp.n_out = ctx->n_strip_targets;
+    fp.strip_rows = ctx->strip_rows;
+    for (int i = 0; i < 8; i++) fp.outs[i] = ctx->strip_targets[i];
+  }
   fp.ray_counters = ctx->d_ray_counters;
   if (ctx->d_ray_counters && band_row0 < 0)
     RT_CUDA(ctx, cudaMemsetAsync(ctx->d_ray_counters, 0, 3 * sizeof(unsigned long long), stream), "clearing ray counters");
@@ -1004,6 +1015,57 @@ int rt_gate_next_frame(rt_ctx *ctx, const uint32_t *dev_flag, uint32_t value) {
 uint32_t *rt_device_frame(rt_ctx *ctx) { return ctx ? ctx->d_frame : nullptr; }
 
 size_t rt_frame_slot_words(const rt_ctx *ctx) { return ctx ? (size_t)ctx->cfg.width * ctx->cfg.height + RT_PEER_FLAGS : 0; }
+
+int rt_set_strip_targets(rt_ctx *ctx, uint32_t *const *dev_frames, int n, int strip_rows) {
+  if (!ctx || n < 0 || n > 8 || (n > 1 && (!dev_frames || strip_rows < 16 || strip_rows % 16 != 0))) return RT_ERR_INVALID;
+  ctx->n_strip_targets = n > 1 ? n : 0;
+  ctx->strip_rows = strip_rows;
+  for (int i = 0; i < 8; i++) ctx->strip_targets[i] = (n > 1 && i < n) ? dev_frames[i] : nullptr;
+  return RT_OK;
+}
+
+// Strips phase, phase + n, ... of frame slot `slot` (rows [s*strip_rows, (s+1)*strip_rows) of strip s) into the same rows of
+// host_argb: one 2-D copy for the full strips, one more for a ragged last strip.  Asynchronous on `stream`.
+int rt_read_strips(rt_ctx *ctx, int slot, int strip_rows, int n, int phase, uint32_t *host_argb, void *stream) {
+  if (!ctx || !host_argb || slot < 0 || slot > 1 || n < 1 || phase < 0 || phase >= n || strip_rows < 1) return RT_ERR_INVALID;
+  RT_CUDA(ctx, cudaSetDevice(ctx->cfg.device), "selecting device");
+  cudaStream_t st = stream ? (cudaStream_t)stream : ctx->stream;
+  const size_t W = (size_t)ctx->cfg.width, H = (size_t)ctx->cfg.height;
+  const uint32_t *src = ctx->d_frame + rt_frame_slot_words(ctx) * (size_t)slot;
+  const size_t strip_words = (size_t)strip_rows * W, pitch = sizeof(uint32_t) * strip_words * (size_t)n;
+  const size_t first = (size_t)phase * strip_words;         // word offset of this rank's first strip
+  const size_t total_strips = (H + strip_rows - 1) / strip_rows;
+  if ((size_t)phase >= total_strips) return RT_OK;
+  const size_t mine = (total_strips - phase + n - 1) / n;   // strips phase, phase+n, ... < total_strips
+  const size_t last_strip = (size_t)phase + (mine - 1) * n; // index of my last strip
+  const size_t last_rows = std::min((size_t)strip_rows, H - last_strip * strip_rows);
+  const size_t full = last_rows == (size_t)strip_rows ? mine : mine - 1;
+  if (full > 0)
+    RT_CUDA(ctx, cudaMemcpy2DAsync(host_argb + first, pitch, src + first, pitch, sizeof(uint32_t) * strip_words, full, cudaMemcpyDeviceToHost, st),
+            "reading screen buffer strips");
+  if (full < mine) {
+    const size_t off = last_strip * strip_words;
+    RT_CUDA(ctx, cudaMemcpyAsync(host_argb + off, src + off, sizeof(uint32_t) * last_rows * W, cudaMemcpyDeviceToHost, st), "reading screen buffer strips");
+  }
+  return RT_OK;
+}
+
+int rt_host_register(void *p, size_t bytes) {
+  if (!p || !bytes) return RT_ERR_INVALID;
+  cudaError_t e = cudaHostRegister(p, bytes, cudaHostRegisterPortable);
+  if (e == cudaErrorHostMemoryAlreadyRegistered) {
+    cudaGetLastError();
+    return RT_OK;
+  }
+  return e == cudaSuccess ? RT_OK : RT_ERR_CUDA;
+}
+
+int rt_host_unregister(void *p) {
+  if (!p) return RT_ERR_INVALID;
+  cudaHostUnregister(p);
+  cudaGetLastError();
+  return RT_OK;
+}
 
 int rt_signal_after_frame(rt_ctx *ctx, uint32_t *dev_counter) {
   if (!ctx || !dev_counter) return RT_ERR_INVALID;

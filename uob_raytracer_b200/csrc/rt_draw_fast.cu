@@ -114,7 +114,7 @@ __device__ __forceinline__ void draw_fast_body(const FrameParams &p, const float
   if (tile_x >= p.vis_x1 || tile_x + kTW <= p.vis_x0 || tile_y >= p.vis_y1 || tile_y + kTH <= p.vis_y0) {
     // the tile lies outside the projection of the scene's bounding box (at 16:9 the bands beside the Cornell box,
     // 44 % of the frame): A*A black samples per pixel (kernels.cl:404-425), without staging or binning anything
-    if (in_frame) p.out[(size_t)y * p.W + x] = 0xff000000u;
+    if (in_frame) frame_of_row(p, y)[(size_t)y * p.W + x] = 0xff000000u;
     return;
   }
 
@@ -259,13 +259,13 @@ __device__ __forceinline__ void draw_fast_body(const FrameParams &p, const float
   const bool spheres_visible = s_spheres_visible != 0;
 #endif
 #ifdef RT_DEBUG_PROLOGUE_ONLY  // experiment: cost of staging + binning alone
-  if (in_frame) p.out[(size_t)y * p.W + x] = 0xff000000u | (unsigned)sc.n_prim;
+  if (in_frame) frame_of_row(p, y)[(size_t)y * p.W + x] = 0xff000000u | (unsigned)sc.n_prim;
   return;
 #endif
   if (sc.n_prim == 0 && !spheres_visible) {
     // nothing can be hit from this tile (at 1080p 44 % of the frame lies beside the box): every ray misses, the
     // pixel is the average of A*A black samples (kernels.cl:404-425)
-    if (in_frame) p.out[(size_t)y * p.W + x] = 0xff000000u;
+    if (in_frame) frame_of_row(p, y)[(size_t)y * p.W + x] = 0xff000000u;
     return;
   }
 
@@ -554,11 +554,11 @@ __device__ __forceinline__ void draw_fast_body(const FrameParams &p, const float
   }
   if constexpr (STRICT) {
     const SF fa = SF(__int2float_rn(A * A));
-    p.out[(size_t)y * p.W + x] = pack_argb<SF>(V3<SF>(div_(total_s.x, fa), div_(total_s.y, fa), div_(total_s.z, fa)));
+    frame_of_row(p, y)[(size_t)y * p.W + x] = pack_argb<SF>(V3<SF>(div_(total_s.x, fa), div_(total_s.y, fa), div_(total_s.z, fa)));
     return;
   }
   const float ia = 1.0f / (float)(A * A);
-  p.out[(size_t)y * p.W + x] = pack_argb<float>(V3<float>(total.x * ia, total.y * ia, total.z * ia));
+  frame_of_row(p, y)[(size_t)y * p.W + x] = pack_argb<float>(V3<float>(total.x * ia, total.y * ia, total.z * ia));
 }
 
 // rt_signal_after_frame: every block makes its stores visible system-wide before it counts itself done; the block that
@@ -596,9 +596,11 @@ __global__ void __launch_bounds__(kThreads, STRICT ? RT_STRICT_MINBLOCKS : RT_MI
   if ((int)blockIdx.x < p.n_split) {
     if (tile_of_block<true, true>(p, (int)blockIdx.x, bx, by)) draw_fast_body<CH, SINGLE, STRICT, true, true>(p, scene, fconst, n, n_sh, bx, by);
   } else {
-    if (tile_of_block<false, true>(p, (int)blockIdx.x - p.n_split, bx, by)) draw_fast_body<CH, SINGLE, STRICT, false, true>(p, scene, fconst, n, n_sh, bx, by);
+    if (tile_of_block<false, true>(p, (int)blockIdx.x - p.n_split, bx, by)) draw_fast_body<CH, SINGLE, STRICT, false, false>(p, scene, fconst, n, n_sh, bx, by);  // no sphere in sight of these tiles
   }
+#ifdef RT_TAIL_SIGNAL  // A/B switch, off: see launch_fast_ch
   block_done(p);
+#endif
 }
 
 #define RT_CAT2(a, b) a##b
@@ -647,11 +649,15 @@ cudaError_t RT_CAT(launch_fast_ch, RT_FAST_CH)(rt_ctx *ctx, const FrameParams &f
   char name[96];
   snprintf(name, sizeof name, "draw_fast_kernel<%d,%s,%s,%s>", CH, single ? "true" : "false", strict ? "true" : "false",
            mode == kSplitHeavy ? "mixed" : (mode == kSplitAll ? "split" : "plain"));
-  // rt_signal_after_frame: the mixed kernel (what a share of a frame on several GPUs runs) reports the delivery itself, from
-  // its last block; behind the other kernels a one-thread kernel does (an exit path through a block-wide barrier costs the
-  // plain kernel 48 bytes of stack it does not have)
+  // rt_signal_after_frame: a one-thread kernel behind the draw kernel reports the delivery.  (Folding it into the draw
+  // kernel — last block by an atomic count, -DRT_TAIL_SIGNAL — was measured slower: the exit path through a block-wide
+  // barrier costs the register-bound kernels 48 bytes more stack, 3-7 % of a small launch, more than the 2 us launch saves.)
   uint32_t *signal_behind = nullptr;
+#ifdef RT_TAIL_SIGNAL
   if (mode != kSplitHeavy && fp.signal_flag) {
+#else
+  if (fp.signal_flag) {
+#endif
     signal_behind = fp.signal_flag;
     fp.signal_flag = nullptr;
   }

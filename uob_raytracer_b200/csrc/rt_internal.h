@@ -59,6 +59,8 @@ struct rt_ctx {
   uint64_t launches = 0;
   unsigned long long *d_ray_counters = nullptr;  // RT_FLAG_COUNT_RAYS
   uint32_t *signal_flag = nullptr;               // rt_signal_after_frame: applies to the next draw launch, then cleared
+  uint32_t *strip_targets[8] = {};               // rt_set_strip_targets
+  int n_strip_targets = 0, strip_rows = 0;
   const uint32_t *gate_flag = nullptr;           // rt_gate_next_frame: applies to the next draw launch, then cleared
   uint32_t gate_value = 0;
   const uint32_t *gate_flag_cached[2] = {nullptr, nullptr};  // the flags d_gate_seen[0..1] mirror

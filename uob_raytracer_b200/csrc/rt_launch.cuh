@@ -42,6 +42,11 @@ __device__ __forceinline__ SceneView stage_scene(float4 *smem, const float4 *__r
   return sc;
 }
 
+// Where pixel row y of this launch is stored (FrameParams::outs: strips of rows dealt out over several frame buffers).
+__device__ __forceinline__ uint32_t *frame_of_row(const FrameParams &p, int y) {
+  return p.n_out > 1 ? p.outs[((unsigned)y / (unsigned)p.strip_rows) % (unsigned)p.n_out] : p.out;
+}
+
 // Which tile does this block render?  block = index of the block within its list (blockIdx.x, or blockIdx.x - n_split for
 // the ordinary blocks of a mixed launch); the list is dealt over the ranks of a multi-GPU interleave (blk_stride / blk_phase)
 // and, for ordinary blocks, permuted by the launch-order table.  (bx, by) = tile coordinates on the launch's tile grid

@@ -51,6 +51,11 @@ struct FrameParams {
   float rot[9];    // rows r0, r1, r2 (skeleton.cpp:149-151)
   float cam[3], light[3];
   uint32_t *out;   // whole-frame ARGB buffer (may be a peer pointer)
+  // Parallel egress (rt_set_strip_targets): frame rows are dealt out in strips of strip_rows rows over n_out owners — row y
+  // belongs to outs[(y / strip_rows) % n_out], the whole-frame buffer of that owner (its own, or a peer's over NVLink) — so
+  // that every GPU ends up with the strips it will copy to the host over its own PCIe link.  n_out <= 1: everything to out.
+  int n_out, strip_rows;
+  uint32_t *outs[8];
   // RT_FLAG_COUNT_RAYS: {primary, shadow, bounce} rays traced, SURVEY.md §8d definition (else NULL)
   unsigned long long *ray_counters;
 };

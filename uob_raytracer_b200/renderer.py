@@ -194,6 +194,16 @@ class Renderer:
     def read_frame_slot_host_ptr(self, slot: int, host_ptr: int) -> None:
         self._check(self._lib.rt_read_frame_slot(self._ctx, slot, host_ptr))
 
+    def set_strip_targets(self, frame_ptrs, strip_rows: int) -> None:
+        """Deal the rows out over several whole-frame buffers (parallel egress): row y -> frame_ptrs[(y // strip_rows) % n]."""
+        n = len(frame_ptrs)
+        arr = (ctypes.c_void_p * max(n, 1))(*[int(p) for p in frame_ptrs])
+        self._check(self._lib.rt_set_strip_targets(self._ctx, arr, n, strip_rows))
+
+    def read_strips(self, slot: int, strip_rows: int, n: int, phase: int, host_ptr: int, stream: int = 0) -> None:
+        """Asynchronous copy of strips phase, phase + n, ... of frame slot `slot` into the same rows of a host frame."""
+        self._check(self._lib.rt_read_strips(self._ctx, slot, strip_rows, n, phase, host_ptr, stream or None))
+
     def set_stream(self, stream: int) -> None:
         """Use the caller's cudaStream_t (0 = back to the context's own) for everything that follows."""
         self._check(self._lib.rt_set_stream(self._ctx, stream or None))
