@@ -239,7 +239,17 @@ int rt_read_frame_slot(rt_ctx *ctx, int slot, uint32_t *host_argb);
  * have registered (rt_host_register on a shared mapping), the N copies run side by side.  n <= 1 switches it off.
  * Tuned brute-force kernels only. */
 int rt_set_strip_targets(rt_ctx *ctx, uint32_t *const *dev_frames, int n, int strip_rows);
+/* "everything queued on the stream so far is visible system-wide, then *dev_counters[i] += 1 for i < n" (n <= 8): one
+ * small kernel that reports a delivery to several strip owners at once. */
+int rt_peer_add(rt_ctx *ctx, uint32_t *const *dev_counters, int n, void *stream);
 int rt_read_strips(rt_ctx *ctx, int slot, int strip_rows, int n, int phase, uint32_t *host_argb, void *stream);
+/* One parallel-egress frame in one call, asynchronous on the context's stream: rows of frame slot `slot` dealt out over
+ * dev_frames[0..n) (slot 0 bases, e.g. rt_device_frame / rt_ipc_open_frame), draw, report the delivery to the other owners,
+ * wait for `deliveries_expected` deliveries into this rank's strips ((n - 1) per frame that has used the slot), copy this
+ * rank's strips into host_argb.  Then rt_synchronize and a barrier of the ranks' hosts complete the frame. */
+int rt_render_strips(rt_ctx *ctx, const float rot12[12], const float cam[4], const float light[4], float focal_length,
+                     uint32_t *const *dev_frames, int n, int rank, int strip_rows, int slot, uint32_t deliveries_expected,
+                     uint32_t *host_argb);
 int rt_host_register(void *p, size_t bytes);
 int rt_host_unregister(void *p);
 

@@ -77,6 +77,9 @@ RT_SYMBOLS = {
     "rt_read_frame_slot": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p]),
     "rt_set_strip_targets": (ctypes.c_int, [ctypes.c_void_p, ctypes.POINTER(ctypes.c_void_p), ctypes.c_int, ctypes.c_int]),
     "rt_read_strips": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p]),
+    "rt_peer_add": (ctypes.c_int, [ctypes.c_void_p, ctypes.POINTER(ctypes.c_void_p), ctypes.c_int, ctypes.c_void_p]),
+    "rt_render_strips": (ctypes.c_int, [ctypes.c_void_p, c_float_p, c_float_p, c_float_p, ctypes.c_float, ctypes.POINTER(ctypes.c_void_p), ctypes.c_int,
+                                        ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_uint32, ctypes.c_void_p]),
     "rt_host_register": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_size_t]),
     "rt_host_unregister": (ctypes.c_int, [ctypes.c_void_p]),
     "rt_debug_visible_rect": (ctypes.c_int, [ctypes.c_void_p, c_float_p, c_float_p, c_float_p, c_float_p, ctypes.c_float,

@@ -1050,6 +1050,29 @@ int rt_read_strips(rt_ctx *ctx, int slot, int strip_rows, int n, int phase, uint
   return RT_OK;
 }
 
+// One parallel-egress frame in one call (what a host loop does per frame on every rank, without six trips through the
+// binding): deal the rows of frame slot `slot` out over dev_frames (rt_set_strip_targets), draw, report the delivery to the
+// other owners, wait until the other ranks have delivered into this rank's strips, copy them into host_argb.  Asynchronous
+// on the context's stream; the caller synchronises (rt_synchronize) and then meets the other ranks.
+int rt_render_strips(rt_ctx *ctx, const float rot12[12], const float cam[4], const float light[4], float focal, uint32_t *const *dev_frames,
+                     int n, int rank, int strip_rows, int slot, uint32_t deliveries_expected, uint32_t *host_argb) {
+  if (!ctx || !dev_frames || n < 2 || n > 8 || rank < 0 || rank >= n || slot < 0 || slot > 1 || !host_argb) return RT_ERR_INVALID;
+  const size_t slot_words = rt_frame_slot_words(ctx), frame_words = (size_t)ctx->cfg.width * ctx->cfg.height;
+  uint32_t *frames[8], *counters[8];
+  int nc = 0;
+  for (int k = 0; k < n; k++) {
+    frames[k] = dev_frames[k] + slot_words * (size_t)slot;
+    if (k != rank) counters[nc++] = frames[k] + frame_words;  // word 0 behind the pixels: deliveries counted
+  }
+  int rc = rt_set_strip_targets(ctx, frames, n, strip_rows);
+  if (rc != RT_OK) return rc;
+  rc = rt_render_device(ctx, rot12, cam, light, focal, frames[rank], nullptr);
+  if (rc == RT_OK) rc = rt_peer_add(ctx, counters, nc, nullptr);
+  if (rc == RT_OK) rc = rt_stream_wait_geq(ctx, frames[rank] + frame_words, deliveries_expected, nullptr);
+  if (rc == RT_OK) rc = rt_read_strips(ctx, slot, strip_rows, n, rank, host_argb, nullptr);
+  return rc;
+}
+
 int rt_host_register(void *p, size_t bytes) {
   if (!p || !bytes) return RT_ERR_INVALID;
   cudaError_t e = cudaHostRegister(p, bytes, cudaHostRegisterPortable);
@@ -1064,6 +1087,14 @@ int rt_host_unregister(void *p) {
   if (!p) return RT_ERR_INVALID;
   cudaHostUnregister(p);
   cudaGetLastError();
+  return RT_OK;
+}
+
+int rt_peer_add(rt_ctx *ctx, uint32_t *const *dev_counters, int n, void *stream) {
+  if (!ctx || !dev_counters || n < 1 || n > 8) return RT_ERR_INVALID;
+  RT_CUDA(ctx, cudaSetDevice(ctx->cfg.device), "selecting device");
+  RT_CUDA(ctx, rt::launch_peer_add_many(dev_counters, n, stream ? (cudaStream_t)stream : ctx->stream), "enqueueing peer signal");
+  ctx->launches++;
   return RT_OK;
 }
 

@@ -49,8 +49,12 @@ __device__ __forceinline__ void resolve_bounces_coop(const FrameParams &p, const
     if (want) {
       bounce++;
       V3<T> ndir;
-      if (hit.color.w == 0.0f) reflect_ray<T>(dir, hit.normal, hit.point, start, ndir, medium);
-      else refract_ray<T>(dir, hit.normal, hit.point, medium, start, ndir, medium);
+      if constexpr (is_strict<T>::value) {
+        if (hit.color.w == 0.0f) reflect_ray<T>(dir, hit.normal, hit.point, start, ndir, medium);
+        else refract_ray<T>(dir, hit.normal, hit.point, medium, start, ndir, medium);
+      } else {
+        bounce_ray_fixed(hit.color.w == 0.0f, dir, hit.normal, hit.point, medium, start, ndir);
+      }
       dir = ndir;
       hit.id = -1;
       hit.color.w = 1.0f;
@@ -527,8 +531,7 @@ __device__ __forceinline__ void draw_fast_body(const FrameParams &p, const float
         if (bounce >= p.B) break;
         bounce++;
         V3<float> start, ndir;
-        if (hit.color.w == 0.0f) reflect_ray<float>(dir, hit.normal, hit.point, start, ndir, medium);
-        else refract_ray<float>(dir, hit.normal, hit.point, medium, start, ndir, medium);
+        bounce_ray_fixed(hit.color.w == 0.0f, dir, hit.normal, hit.point, medium, start, ndir);
         dir = ndir;
         hit.id = -1;
         hit.color.w = 1.0f;

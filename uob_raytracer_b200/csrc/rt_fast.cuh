@@ -314,6 +314,35 @@ __device__ __forceinline__ void primary_triangles(const FastScene &sc, V3<float>
 // share out the triangles of ONE ray at a time) — same per-triangle arithmetic, same winner, hence the same bits.
 // ---------------------------------------------------------------------------------------------
 
+// Sphere part of a bounce ray's closest hit and the mirror / glass bounce itself, fast policy: evaluated in the strict
+// arithmetic (every operation separately rounded).  They are a few dozen operations on one ray in a hundred, and they are
+// inlined into several search loops — with plain float operators each copy would be free to contract differently, and the
+// frame would depend on which copy a ray went through (lane mapping, partition over GPUs).
+__device__ __forceinline__ V3<sfloat> to_strict(V3<float> v) { return V3<sfloat>(sfloat(v.x), sfloat(v.y), sfloat(v.z)); }
+__device__ __forceinline__ V3<float> to_fast(V3<sfloat> v) { return V3<float>(v.x.v, v.y.v, v.z.v); }
+__device__ __forceinline__ void closest_spheres_fixed(V3<float> start, V3<float> dir, float current_t, HitRec<float> &hit) {
+  HitRec<sfloat> hs;
+  hs.id = -1;
+  hs.color = make_float4(0.0f, 0.0f, 0.0f, 1.0f);
+  hs.point = V3<sfloat>(sfloat(0.0f), sfloat(0.0f), sfloat(0.0f));
+  hs.normal = hs.point;
+  closest_spheres<sfloat>(to_strict(start), to_strict(dir), sfloat(current_t), hs);
+  if (hs.id == -2) {
+    hit.id = -2;
+    hit.point = to_fast(hs.point);
+    hit.normal = to_fast(hs.normal);
+    hit.color = hs.color;
+  }
+}
+__device__ __forceinline__ void bounce_ray_fixed(bool mirror, V3<float> dir, V3<float> normal, V3<float> point, float &medium, V3<float> &start,
+                                                 V3<float> &ndir) {
+  V3<sfloat> s, d;
+  if (mirror) reflect_ray<sfloat>(to_strict(dir), to_strict(normal), to_strict(point), s, d, medium);
+  else refract_ray<sfloat>(to_strict(dir), to_strict(normal), to_strict(point), medium, s, d, medium);
+  start = to_fast(s);
+  ndir = to_fast(d);
+}
+
 // One candidate of the fast policy: (t, u, v) of triangle i for the ray (start, dir), or false.  The inside test runs on
 // sign-corrected triple products, t = ts / |dn|.  Two plane tests that cost one 16-byte load and six FMAs come first:
 //   dn = d.N, bn = (o - v0).N = o.N - v0.N:   t = -bn/dn < 0 (the plane lies behind the ray)  -> no candidate
@@ -321,22 +350,31 @@ __device__ __forceinline__ void primary_triangles(const FastScene &sc, V3<float>
 // (t_limit = the current best of a sequential scan, which would reject the candidate anyway; RT_MAXFLOAT = no limit).
 __device__ __forceinline__ bool bounce_candidate(const SceneView &sc, int i, V3<float> start, V3<float> dir, float t_limit, float &t, float &u,
                                                  float &v) {
+  // every operation spelled out (fmaf / __fmul_rn / __fsub_rn): this function is inlined into the lane-parallel and the
+  // warp-cooperative search, and the two copies must round alike — the frame may not depend on which one a ray took
   const float4 P = sc.tnd[i];
-  const float dn = fmaf(dir.x, P.x, fmaf(dir.y, P.y, dir.z * P.z));
+  const float dn = fmaf(dir.x, P.x, fmaf(dir.y, P.y, __fmul_rn(dir.z, P.z)));
   const float bn = fmaf(start.x, P.x, fmaf(start.y, P.y, fmaf(start.z, P.z, -P.w)));
   const unsigned sb = __float_as_uint(dn) & 0x80000000u;
   const float ts = xor_sign(-bn, sb), adn = fabsf(dn);
-  if (!(ts >= 0.0f) || ts > t_limit * adn * 1.0001f) return false;  // (NaN rays fail the first test, as they fail the full one)
+  if (!(ts >= 0.0f) || ts > __fmul_rn(__fmul_rn(t_limit, adn), 1.0001f)) return false;  // (NaN rays fail the first test, as they fail the full one)
   const float4 A = sc.ta[i], Bq = sc.tb[i], C = sc.tc[i];
-  const V3<float> b(start.x - A.x, start.y - A.y, start.z - A.z), e1(Bq.x, Bq.y, Bq.z), e2(C.x, C.y, C.z);
-  const V3<float> q(b.y * dir.z - b.z * dir.y, b.z * dir.x - b.x * dir.z, b.x * dir.y - b.y * dir.x);
-  const float us = xor_sign(-dot(e2, q), sb), vs = xor_sign(dot(e1, q), sb);
-  if (!((us >= 0.0f) & (vs >= 0.0f) & ((us + vs) <= adn))) return false;
+  const float bx = __fsub_rn(start.x, A.x), by = __fsub_rn(start.y, A.y), bz = __fsub_rn(start.z, A.z);
+  const float qx = fmaf(by, dir.z, -__fmul_rn(bz, dir.y)), qy = fmaf(bz, dir.x, -__fmul_rn(bx, dir.z)), qz = fmaf(bx, dir.y, -__fmul_rn(by, dir.x));
+  const float eu = fmaf(C.x, qx, fmaf(C.y, qy, __fmul_rn(C.z, qz))), ev = fmaf(Bq.x, qx, fmaf(Bq.y, qy, __fmul_rn(Bq.z, qz)));
+  const float us = xor_sign(-eu, sb), vs = xor_sign(ev, sb);
+  if (!((us >= 0.0f) & (vs >= 0.0f) & (__fadd_rn(us, vs) <= adn))) return false;
   const float inv = __frcp_rn(adn);
-  t = ts * inv;
-  u = us * inv;
-  v = vs * inv;
+  t = __fmul_rn(ts, inv);
+  u = __fmul_rn(us, inv);
+  v = __fmul_rn(vs, inv);
   return true;
+}
+
+// (v0 + u e1) + v e2 of the winning triangle (kernels.cl:124), fast policy, spelled out for the same reason
+__device__ __forceinline__ V3<float> bounce_hit_point(const SceneView &sc, int i, float u, float v) {
+  const float4 A = sc.ta[i], Bq = sc.tb[i], C = sc.tc[i];
+  return V3<float>(fmaf(v, C.x, fmaf(u, Bq.x, A.x)), fmaf(v, C.y, fmaf(u, Bq.y, A.y)), fmaf(v, C.z, fmaf(u, Bq.z, A.z)));
 }
 
 // Lane-parallel search.  Fast policy: a bounce ray inside the box faces about half the planes and, once it has a hit, most
@@ -414,11 +452,13 @@ template <class T>
 __device__ __forceinline__ void finish_closest(const SceneView &sc, V3<T> start, V3<T> dir, const ClosestState<T> &cs, HitRec<T> &hit) {
   if (cs.id >= 0) {
     hit.id = cs.id;
-    hit.point = hit_point<T>(sc.ta[cs.id], sc.tb[cs.id], sc.tc[cs.id], cs.u, cs.v);
+    if constexpr (is_strict<T>::value) hit.point = hit_point<T>(sc.ta[cs.id], sc.tb[cs.id], sc.tc[cs.id], cs.u, cs.v);
+    else hit.point = bounce_hit_point(sc, cs.id, cs.u, cs.v);
     hit.normal = xyz<T>(sc.tn[cs.id]);
     hit.color = sc.tcol[cs.id];
   }
-  closest_spheres<T>(start, dir, cs.t, hit);
+  if constexpr (is_strict<T>::value) closest_spheres<T>(start, dir, cs.t, hit);
+  else closest_spheres_fixed(start, dir, cs.t, hit);
 }
 
 // Closest hit of a bounce ray, fast policy (kernels.cl:168-241), lane-parallel, in one piece (the form the full-size
@@ -430,37 +470,24 @@ __device__ __forceinline__ void finish_closest(const SceneView &sc, V3<T> start,
 // A bounce ray inside the box faces about half the planes and, once it has a hit, most of the rest lie behind it; the
 // rays of a warp leave neighbouring points of a sphere, so they mostly agree.  Only survivors load the vertices.
 __device__ __forceinline__ void closest_hit_bounce(const SceneView &sc, V3<float> start, V3<float> dir, HitRec<float> &hit) {
-  ClosestState<float> cs;
-  cs.reset();
+  int best = -1;
+  float bt = RT_MAXFLOAT, bu = 0.0f, bv = 0.0f;
   for (int i = 0; i < sc.n; i++) {
-    const float4 P = sc.tnd[i];
-    const float dn = fmaf(dir.x, P.x, fmaf(dir.y, P.y, dir.z * P.z));
-    const float bn = fmaf(start.x, P.x, fmaf(start.y, P.y, fmaf(start.z, P.z, -P.w)));
-    const unsigned sb = __float_as_uint(dn) & 0x80000000u;
-    const float ts = xor_sign(-bn, sb), adn = fabsf(dn);
-    if (!(ts >= 0.0f) || ts > cs.t * adn * 1.0001f) continue;  // (NaN rays fail the first test, as they fail the full one)
-    const float4 A = sc.ta[i], Bq = sc.tb[i], C = sc.tc[i];
-    const V3<float> b(start.x - A.x, start.y - A.y, start.z - A.z), e1(Bq.x, Bq.y, Bq.z), e2(C.x, C.y, C.z);
-    const V3<float> q(b.y * dir.z - b.z * dir.y, b.z * dir.x - b.x * dir.z, b.x * dir.y - b.y * dir.x);
-    const float us = xor_sign(-dot(e2, q), sb), vs = xor_sign(dot(e1, q), sb);
-    if ((us >= 0.0f) & (vs >= 0.0f) & ((us + vs) <= adn)) {
-      const float inv = __frcp_rn(adn);
-      const float t = ts * inv;
-      if (t < cs.t) {
-        cs.id = i;
-        cs.u = us * inv;
-        cs.v = vs * inv;
-        cs.t = t;
-      }
+    float t, u, v;
+    if (bounce_candidate(sc, i, start, dir, bt, t, u, v) && t < bt) {  // strict '<', ascending index: lowest index wins a tie
+      best = i;
+      bt = t;
+      bu = u;
+      bv = v;
     }
   }
-  if (cs.id >= 0) {
-    hit.id = cs.id;
-    hit.point = hit_point<float>(sc.ta[cs.id], sc.tb[cs.id], sc.tc[cs.id], cs.u, cs.v);
-    hit.normal = xyz<float>(sc.tn[cs.id]);
-    hit.color = sc.tcol[cs.id];
+  if (best >= 0) {
+    hit.id = best;
+    hit.point = bounce_hit_point(sc, best, bu, bv);
+    hit.normal = xyz<float>(sc.tn[best]);
+    hit.color = sc.tcol[best];
   }
-  closest_spheres<float>(start, dir, cs.t, hit);
+  closest_spheres_fixed(start, dir, bt, hit);
 }
 
 // The S jitters of a pixel: they depend on the pixel id only (kernels.cl:319,331).

@@ -89,6 +89,7 @@ constexpr size_t kDrawStaticSmem = 6144;  // the mixed kernel carries the static
 // rt_peak.cu (small utility kernels)
 cudaError_t launch_peer_signal(uint32_t *flag, uint32_t value, cudaStream_t stream);
 cudaError_t launch_peer_add(uint32_t *counter, cudaStream_t stream);
+cudaError_t launch_peer_add_many(uint32_t *const *counters, int n, cudaStream_t stream);
 cudaError_t launch_peer_wait(const uint32_t *flags, int n, uint32_t value, int *status, cudaStream_t stream);
 // rt_bvh.cu
 cudaError_t bvh_build(rt_ctx *ctx, const float *verts, const float *normals, const float *colors, int n);

@@ -48,15 +48,24 @@ __global__ void peer_wait_kernel(const uint32_t *flags, int n, uint32_t value, i
   __threadfence_system();
 }
 
-__global__ void peer_add_kernel(uint32_t *counter) {
+struct PeerCounters {
+  uint32_t *c[8];
+};
+__global__ void peer_add_kernel(PeerCounters pc) {
+  // Everything this stream did before (the draw kernel's stores into the peers' frames) happened-before this kernel; the
+  // system-scope fence makes it visible to the other GPUs before the count is.
   __threadfence_system();
-  asm volatile("red.release.sys.global.add.u32 [%0], 1;" ::"l"(counter) : "memory");
+  asm volatile("red.release.sys.global.add.u32 [%0], 1;" ::"l"(pc.c[threadIdx.x]) : "memory");
 }
 
-cudaError_t launch_peer_add(uint32_t *counter, cudaStream_t stream) {
-  peer_add_kernel<<<1, 1, 0, stream>>>(counter);
+cudaError_t launch_peer_add_many(uint32_t *const *counters, int n, cudaStream_t stream) {
+  PeerCounters pc{};
+  for (int i = 0; i < n && i < 8; i++) pc.c[i] = counters[i];
+  peer_add_kernel<<<1, n, 0, stream>>>(pc);
   return cudaGetLastError();
 }
+
+cudaError_t launch_peer_add(uint32_t *counter, cudaStream_t stream) { return launch_peer_add_many(&counter, 1, stream); }
 
 cudaError_t launch_peer_signal(uint32_t *flag, uint32_t value, cudaStream_t stream) {
   peer_signal_kernel<<<1, 1, 0, stream>>>(flag, value);

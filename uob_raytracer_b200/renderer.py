@@ -200,6 +200,29 @@ class Renderer:
         arr = (ctypes.c_void_p * max(n, 1))(*[int(p) for p in frame_ptrs])
         self._check(self._lib.rt_set_strip_targets(self._ctx, arr, n, strip_rows))
 
+    def peer_add(self, counter_ptrs, stream: int = 0) -> None:
+        """One small kernel: everything queued so far is visible system-wide, then each counter += 1."""
+        n = len(counter_ptrs)
+        arr = (ctypes.c_void_p * n)(*[int(p) for p in counter_ptrs])
+        self._check(self._lib.rt_peer_add(self._ctx, arr, n, stream or None))
+
+    def render_strips(self, rot12, cam4, light4, focal: float, frame_bases, rank: int, strip_rows: int, slot: int, deliveries_expected: int,
+                      host_ptr: int) -> None:
+        """One parallel-egress frame (rt_render_strips), asynchronous on the context's stream."""
+        n = len(frame_bases)
+        if getattr(self, "_strip_bases_key", None) != tuple(frame_bases):
+            self._strip_bases = (ctypes.c_void_p * n)(*[int(p) for p in frame_bases])
+            self._strip_bases_key = tuple(frame_bases)
+        self._check(self._lib.rt_render_strips(self._ctx, rot12.ctypes.data_as(c_float_p), cam4.ctypes.data_as(c_float_p),
+                                               light4.ctypes.data_as(c_float_p), focal, self._strip_bases, n, rank, strip_rows, slot,
+                                               deliveries_expected, host_ptr))
+
+    def host_register(self, ptr: int, nbytes: int) -> None:
+        self._check(self._lib.rt_host_register(ptr, nbytes))
+
+    def host_unregister(self, ptr: int) -> None:
+        self._lib.rt_host_unregister(ptr)
+
     def read_strips(self, slot: int, strip_rows: int, n: int, phase: int, host_ptr: int, stream: int = 0) -> None:
         """Asynchronous copy of strips phase, phase + n, ... of frame slot `slot` into the same rows of a host frame."""
         self._check(self._lib.rt_read_strips(self._ctx, slot, strip_rows, n, phase, host_ptr, stream or None))
