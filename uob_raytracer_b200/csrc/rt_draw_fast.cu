@@ -515,7 +515,7 @@ __device__ __forceinline__ void draw_fast_body(const FrameParams &p, const float
             make_jitters_shared<CH, kThreads, false>(global_id, jit);
             have_jit = true;
           }
-          const float fl = gain * (RT_INDIRECT + direct_light_fast<CH, SINGLE, JittersShared<CH, kThreads>>(sc, hit.point, hit.normal, light, S, global_id, jit));
+          const float fl = __fmul_rn(gain, __fadd_rn(RT_INDIRECT, direct_light_fast<CH, SINGLE, JittersShared<CH, kThreads>>(sc, hit.point, hit.normal, light, S, global_id, jit)));
           // product and sum rounded separately: the split mapping parks the product and adds it later, and every
           // lane mapping (hence every multi-GPU partition) has to produce the same bits
           const V3<float> contrib(__fmul_rn(hit.color.x, fl), __fmul_rn(hit.color.y, fl), __fmul_rn(hit.color.z, fl));
@@ -561,7 +561,7 @@ __device__ __forceinline__ void draw_fast_body(const FrameParams &p, const float
     return;
   }
   const float ia = 1.0f / (float)(A * A);
-  frame_of_row(p, y)[(size_t)y * p.W + x] = pack_argb<float>(V3<float>(total.x * ia, total.y * ia, total.z * ia));
+  frame_of_row(p, y)[(size_t)y * p.W + x] = pack_argb<float>(V3<float>(__fmul_rn(total.x, ia), __fmul_rn(total.y, ia), __fmul_rn(total.z, ia)));
 }
 
 // rt_signal_after_frame: every block makes its stores visible system-wide before it counts itself done; the block that

@@ -609,7 +609,7 @@ __device__ __forceinline__ int shadow_lit_count(const FastScene &sc, V3<float> s
 #pragma unroll
       for (int k = 0; k < CH; k++) {
         const float ddx = r.x + j.jx(k), ddy = r.y + j.jy(k), ddz = r.z + j.jz(k);
-        dd[k] = (ddx * ddx + ddy * ddy) + ddz * ddz;
+        dd[k] = fmaf(ddz, ddz, fmaf(ddx, ddx, __fmul_rn(ddy, ddy)));
       }
     }
   };
@@ -627,15 +627,17 @@ __device__ __forceinline__ int shadow_lit_count(const FastScene &sc, V3<float> s
     const float4 Q0 = q[0], Q1 = q[1];
     const V3<float> b(start.x - Q0.x, start.y - Q0.y, start.z - Q0.z);
     const float c0 = Q1.x, c1 = Q1.y, c2 = Q1.z;
-    const float num = (b.x * c0 - b.y * c1) + b.z * c2;  // det[b,e1,e2] = b.N
-    const float rN = (r.x * c0 - r.y * c1) + r.z * c2;   // r.N   (det A of sample k = -(rN + j_k.N))
+    // (everything a per-sample decision or the pixel value depends on is spelled out — fmaf / __fmul_rn — so that every
+    // instantiation of this function rounds alike: the frame may not depend on which kernel a tile went through)
+    const float num = fmaf(b.z, c2, fmaf(b.x, c0, -__fmul_rn(b.y, c1)));  // det[b,e1,e2] = b.N
+    const float rN = fmaf(r.z, c2, fmaf(r.x, c0, -__fmul_rn(r.y, c1)));   // r.N   (det A of sample k = -(rN + j_k.N))
     const float w = xor_sign(rN, __float_as_uint(num) & 0x80000000u);
     if (fabsf(num) >= (Q0.w - w) * kk) continue;  // plane cull: no sample passes stage 1
     const float4 Q2 = q[2], Q3 = q[3];
     const V3<float> e1(Q2.x, Q2.y, Q2.z), e2(Q3.x, Q3.y, Q3.z);
-    const V3<float> U(b.y * e2.z - b.z * e2.y, b.z * e2.x - b.x * e2.z, b.x * e2.y - b.y * e2.x);  // b x e2
-    const V3<float> V(e1.y * b.z - e1.z * b.y, e1.z * b.x - e1.x * b.z, e1.x * b.y - e1.y * b.x);  // e1 x b
-    const float rU = dot(r, U), rV = dot(r, V);
+    const V3<float> U(fmaf(b.y, e2.z, -__fmul_rn(b.z, e2.y)), fmaf(b.z, e2.x, -__fmul_rn(b.x, e2.z)), fmaf(b.x, e2.y, -__fmul_rn(b.y, e2.x)));  // b x e2
+    const V3<float> V(fmaf(e1.y, b.z, -__fmul_rn(e1.z, b.y)), fmaf(e1.z, b.x, -__fmul_rn(e1.x, b.z)), fmaf(e1.x, b.y, -__fmul_rn(e1.y, b.x)));  // e1 x b
+    const float rU = fmaf(r.z, U.z, fmaf(r.y, U.y, __fmul_rn(r.x, U.x))), rV = fmaf(r.z, V.z, fmaf(r.y, V.y, __fmul_rn(r.x, V.x)));
     const float arN = fabsf(rN);
     if (arN > Q0.w) {
       // every sample has sign(dn) = sign(rN): edge cull on the un-jittered ray
@@ -645,7 +647,7 @@ __device__ __forceinline__ int shadow_lit_count(const FastScene &sc, V3<float> s
       const float eu = xor_sign(rU, sg), ev = xor_sign(rV, sg);
       if ((eu < -mU) | (ev < -mV) | ((eu + ev) - (mU + mV) > arN + Q0.w)) continue;
     }
-    const float q1 = num * num * inv_r2;  // t^2 |d|^2 < r^2  <=>  q1 |d|^2 < dn^2
+    const float q1 = __fmul_rn(__fmul_rn(num, num), inv_r2);  // t^2 |d|^2 < r^2  <=>  q1 |d|^2 < dn^2
     const unsigned numb = __float_as_uint(num);
     need_dd();
     // det A = -dn;  t = -num/dn;  u = E1/dn;  v = E2/dn
@@ -685,7 +687,7 @@ __device__ __forceinline__ int shadow_lit_count(const FastScene &sc, V3<float> s
         const float E2 = fmaf(jx, V.x, fmaf(jy, V.y, fmaf(jz, V.z, rV)));
         const unsigned dnb = __float_as_uint(dn);
         const unsigned sx = ((__float_as_uint(E1) ^ dnb) | (__float_as_uint(E2) ^ dnb)) | ~(numb ^ dnb);
-        const bool hit = ((int)sx >= 0) & (fabsf(E1 + E2) <= fabsf(dn)) & (q1 * dd[k] < dn * dn);
+        const bool hit = ((int)sx >= 0) & (fabsf(__fadd_rn(E1, E2)) <= fabsf(dn)) & (__fmul_rn(q1, dd[k]) < __fmul_rn(dn, dn));
         occ |= hit ? (1u << k) : 0u;
       }
     }
@@ -696,11 +698,11 @@ __device__ __forceinline__ int shadow_lit_count(const FastScene &sc, V3<float> s
     if (c_sphere_color[i].w == -1.0f) continue;  // glass casts no shadow (kernels.cl:279)
     const float4 cr = c_sphere_center_r2[i];
     const V3<float> L(start.x - cr.x, start.y - cr.y, start.z - cr.z);
-    const float LL = dot(L, L);
-    const float c = LL - cr.w;
+    const float LL = fmaf(L.z, L.z, fmaf(L.y, L.y, __fmul_rn(L.x, L.x)));
+    const float c = __fsub_rn(LL, cr.w);
     // Cone cull: the distance from the centre to the line (start, d_s) is at least
     // perp_c - |L| |d_s/|d_s| - r/|r||  >=  perp_c - |L| jmax/(R - jmax); no real root if that exceeds the radius.
-    const float Lr = dot(L, r);
+    const float Lr = fmaf(L.z, r.z, fmaf(L.y, r.y, __fmul_rn(L.x, r.x)));
     const float perp2 = LL - Lr * Lr * inv_r2;
     const float lim = kSlack * sqrt_approx(cr.w) + sqrt_approx(LL) * (kk * kJitterMax * rcp_approx(R));
     if (perp2 > lim * lim) continue;
@@ -709,16 +711,16 @@ __device__ __forceinline__ int shadow_lit_count(const FastScene &sc, V3<float> s
     for (int k = 0; k < CH; k++) {
       if ((occ >> k) & 1u) continue;
       const float a = dd_of(k);
-      const float b = 2.0f * fmaf(j.jx(k), L.x, fmaf(j.jy(k), L.y, fmaf(j.jz(k), L.z, Lr)));
-      const float disc = b * b - 4.0f * a * c;
+      const float b = __fmul_rn(2.0f, fmaf(j.jx(k), L.x, fmaf(j.jy(k), L.y, fmaf(j.jz(k), L.z, Lr))));
+      const float disc = fmaf(b, b, -__fmul_rn(__fmul_rn(4.0f, a), c));
       if (disc < 0.0f) continue;
       const float sq = sqrt_approx(disc);
-      const float qq = (b > 0.0f) ? -0.5f * (b + sq) : -0.5f * (b - sq);
-      const float x0 = qq * rcp_approx(a);
-      const float x1 = c * rcp_approx(qq);
+      const float qq = (b > 0.0f) ? __fmul_rn(-0.5f, __fadd_rn(b, sq)) : __fmul_rn(-0.5f, __fsub_rn(b, sq));
+      const float x0 = __fmul_rn(qq, rcp_approx(a));
+      const float x1 = __fmul_rn(c, rcp_approx(qq));
       const float x_min = fminf(x0, x1), x_max = fmaxf(x0, x1);
       // |x d|^2 < r^2
-      if ((x_min >= 0.0f && x_min * x_min * a < radius_sq) || (x_max >= 0.0f && x_max * x_max * a < radius_sq)) occ |= 1u << k;
+      if ((x_min >= 0.0f && __fmul_rn(__fmul_rn(x_min, x_min), a) < radius_sq) || (x_max >= 0.0f && __fmul_rn(__fmul_rn(x_max, x_max), a) < radius_sq)) occ |= 1u << k;
     }
   }
   return CH - __popc(occ);
@@ -730,9 +732,9 @@ template <int CH, bool SINGLE, class J>
 __device__ __forceinline__ float direct_light_fast(const FastScene &sc, V3<float> point, V3<float> normal, V3<float> light_pos, int S,
                                                    int global_id, const J &jit) {
   const V3<float> r = light_pos - point;
-  const V3<float> start = point + scale(RT_BIAS, r);
-  const float radius_sq = (r.x * r.x + r.y * r.y) + r.z * r.z;
-  const float lam = RT_LIGHT_COLOR * fmaxf(dot(r, normal), 0.0f);
+  const V3<float> start(fmaf(RT_BIAS, r.x, point.x), fmaf(RT_BIAS, r.y, point.y), fmaf(RT_BIAS, r.z, point.z));
+  const float radius_sq = fmaf(r.z, r.z, fmaf(r.y, r.y, __fmul_rn(r.x, r.x)));  // spelled out: see shadow_lit_count
+  const float lam = __fmul_rn(RT_LIGHT_COLOR, fmaxf(fmaf(r.z, normal.z, fmaf(r.y, normal.y, __fmul_rn(r.x, normal.x))), 0.0f));
   // facing away from the light: the result is lit*0/den = 0 whatever the shadow rays find
   if (lam == 0.0f && radius_sq > 0.0f && radius_sq < 1.0e37f) return 0.0f;
   int lit = 0;
@@ -749,7 +751,7 @@ __device__ __forceinline__ float direct_light_fast(const FastScene &sc, V3<float
       lit += shadow_lit_count<CH, Jitters<CH>>(sc, start, r, radius_sq, jj, valid);
     }
   }
-  return (float)lit * lam * rcp_approx(4.0f * RT_PI_F * radius_sq * (float)S);
+  return __fmul_rn(__fmul_rn((float)lit, lam), rcp_approx(__fmul_rn(__fmul_rn(4.0f * RT_PI_F, radius_sq), (float)S)));
 }
 
 // ---------------------------------------------------------------------------------------------

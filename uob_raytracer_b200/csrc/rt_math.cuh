@@ -110,7 +110,7 @@ template <class T> __device__ __forceinline__ T crush1(uint32_t v, float range) 
     return div_(T(range) * T(__uint2float_rn(v)), T(4294967296.0f)) - T(range / 2.f);
   } else {
     // division by 2^32 is an exact scaling, so this is the same value with one rounding less
-    return __uint2float_rn(v) * (range * 2.3283064365386963e-10f) - range * 0.5f;
+    return fmaf(__uint2float_rn(v), range * 2.3283064365386963e-10f, -(range * 0.5f));  // (spelled out: every copy rounds alike)
   }
 }
 
