@@ -4,10 +4,11 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import uob_raytracer_b200 as u
 name = sys.argv[1] if len(sys.argv) > 1 else "cfg2"
 n = int(sys.argv[2]) if len(sys.argv) > 2 else 4
+strict = len(sys.argv) > 3 and sys.argv[3] == "strict"
 cfg = u.CONFIGS[name]
 scene = u.load_test_model()
 cam = u.Camera()
-with u.Renderer(cfg.width, cfg.height, cfg.aa, cfg.shadow_samples, cfg.max_bounces) as r:
+with u.Renderer(cfg.width, cfg.height, cfg.aa, cfg.shadow_samples, cfg.max_bounces, strict=strict) as r:
     r.upload_scene(scene)
     for _ in range(n):
         r.render_device(cam.rot(), cam.position, cam.light, cfg.focal)

@@ -139,7 +139,11 @@ __device__ __forceinline__ void draw_fast_body(const FrameParams &p, const float
   // single-rounded operations, done once per frame instead of once per block: 0.32 -> 0.30 ms on cfg2); the fast kernels
   // compute them in the block prologue as before — measured: the extra pointer and loads cost them 64 bytes more stack
   // (they are register-bound at 80 registers, three blocks per SM) and 5 % (cfg2) to 17 % (cfg3) of their speed.
+#ifdef RT_HOST_CONSTS_FAST
+  constexpr bool kHC = RT_HOST_CONSTS;
+#else
   constexpr bool kHC = STRICT && RT_HOST_CONSTS;
+#endif
   if constexpr (kHC)
     for (int i = threadIdx.x; i < 6 * n; i += kThreads) prim[i] = fconst[i];
   for (int i = threadIdx.x; i < 5 * n_sh + n; i += kThreads) shad[i] = scene[5 * n + 3 * n_sh + i];  // records, bounding spheres, plane records

@@ -550,7 +550,7 @@ __device__ __forceinline__ void make_jitters_shared(int global_id, const Jitters
   uint32_t rx, ry, rz;
   seed_rng(global_id, rx, ry, rz);
   if constexpr (JittersShared<CH, STRIDE>::kPacked) {
-#pragma unroll
+#pragma unroll 1
     for (int k2 = 0; k2 < CH / 2; k2++) {
       float2 vx, vy, vz;
       rx = xorshift32(rx);
@@ -570,7 +570,8 @@ __device__ __forceinline__ void make_jitters_shared(int global_id, const Jitters
       *reinterpret_cast<float2 *>(jit.p + 2 * STRIDE * (2 * (CH / 2) + k2)) = vz;
     }
   } else {
-#pragma unroll
+    // (two samples per trip: fully unrolled, the compiler computes all 3 CH values first and parks them in local memory)
+#pragma unroll 2
     for (int k = 0; k < CH; k++) {
       rx = xorshift32(rx);
       ry = xorshift32(ry);
