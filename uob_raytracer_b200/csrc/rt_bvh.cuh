@@ -118,11 +118,16 @@ template <class T> struct BvhTracer {
     if (bv.n_bvh > 0) {
       const float ox = raw(start.x), oy = raw(start.y), oz = raw(start.z);
       const float ix = safe_rcp_dir(raw(dir.x)), iy = safe_rcp_dir(raw(dir.y)), iz = safe_rcp_dir(raw(dir.z));
+      // "while-while" traversal: a lane walks down internal nodes until it holds a leaf (or runs out of nodes); the lanes
+      // of the warp re-converge behind that inner loop and test their leaves TOGETHER.  (With one loop that does either a
+      // node step or a leaf step per trip, the two kinds of step alternate lane by lane and each runs with a handful of
+      // the 32 lanes: ncu showed 4-9 active threads per instruction in the leaf tests.)
       int stack[kBvhStack];
       int sp = 0;
       int ref = bv.root;
-      for (;;) {
-        if (ref >= 0) {
+      bool done = false;
+      while (!done) {
+        while (ref >= 0) {
           const float4 *nd4 = bv.nodes + 4 * (size_t)ref;
           const float4 n0 = __ldg(nd4), n1 = __ldg(nd4 + 1), n2 = __ldg(nd4 + 2), n3 = __ldg(nd4 + 3);
           const float tmax = raw(cs.t);
@@ -133,17 +138,19 @@ template <class T> struct BvhTracer {
             const bool first0 = e0 <= e1;
             if (sp < kBvhStack) stack[sp++] = first0 ? r1 : r0;
             ref = first0 ? r0 : r1;
-            continue;
-          }
-          if (e0 >= 0.0f) {
+          } else if (e0 >= 0.0f) {
             ref = r0;
-            continue;
-          }
-          if (e1 >= 0.0f) {
+          } else if (e1 >= 0.0f) {
             ref = r1;
-            continue;
+          } else if (sp > 0) {
+            ref = stack[--sp];
+          } else {
+            done = true;
+            break;
           }
-        } else {
+        }
+        if (done) break;
+        {
           const int first = (~ref) >> 3, cnt = ((~ref) & 7) + 1;
           for (int k = 0; k < cnt; k++) {
             const int s = first + k;
@@ -194,33 +201,79 @@ template <class T> struct BvhTracer {
       // touches its (padded) box.
       const float ox = raw(start.x), oy = raw(start.y), oz = raw(start.z);
       const float R = sqrtf(raw(radius_sq));
-      float ix[CH], iy[CH], iz[CH], tm[CH];
+      // The CH rays share their origin and differ by a jitter of a few per cent of |r|: ONE interval-arithmetic slab test
+      // per box decides for the whole packet.  Per axis the inverse directions span [lo, hi] (same sign, else the axis
+      // puts no constraint); every ray's entry / exit parameter on that axis lies between the smallest and the largest of
+      // the four products (box face - origin) x {lo, hi}, so  max_axes(smallest) <= min_axes(largest, t_max)  holds for
+      // every ray that touches the box.  Conservative (a few more nodes are visited), a third of the arithmetic of CH
+      // separate tests; the leaves test every live ray exactly as before.
+      // (An axis on which the direction component changes sign within the packet — typical for the two axes across the
+      // beam — bounds no parameter, but the POSITION o + t d does: with t in [0, t_far] it stays within
+      // [o + t_far d_min, o + t_far d_max], which has to overlap the box.)
+      float ilo[3], ihi[3], dlo[3], dhi[3], tmax_all = 0.0f;
+      bool axis_ok[3] = {true, true, true};
+      {
+        const float big = 3.0e38f;
+        dlo[0] = dlo[1] = dlo[2] = big;
+        dhi[0] = dhi[1] = dhi[2] = -big;
 #pragma unroll
-      for (int k = 0; k < CH; k++) {
-        const float dx = raw(rays.d[k].x), dy = raw(rays.d[k].y), dz = raw(rays.d[k].z);
-        ix[k] = safe_rcp_dir(dx);
-        iy[k] = safe_rcp_dir(dy);
-        iz[k] = safe_rcp_dir(dz);
-        tm[k] = 1.0001f * R * rsqrtf(dx * dx + dy * dy + dz * dz);
+        for (int k = 0; k < CH; k++) {
+          const float dx = raw(rays.d[k].x), dy = raw(rays.d[k].y), dz = raw(rays.d[k].z);
+          dlo[0] = fminf(dlo[0], dx);
+          dhi[0] = fmaxf(dhi[0], dx);
+          dlo[1] = fminf(dlo[1], dy);
+          dhi[1] = fmaxf(dhi[1], dy);
+          dlo[2] = fminf(dlo[2], dz);
+          dhi[2] = fmaxf(dhi[2], dz);
+          tmax_all = fmaxf(tmax_all, 1.0001f * R * rsqrtf(dx * dx + dy * dy + dz * dz));
+        }
+#pragma unroll
+        for (int a = 0; a < 3; a++) {
+          // the component keeps its sign and stays away from zero: its inverse spans [1/d_max, 1/d_min]
+          axis_ok[a] = (dlo[a] > 1e-6f) || (dhi[a] < -1e-6f);
+          ilo[a] = axis_ok[a] ? 1.0f / dhi[a] : 0.0f;
+          ihi[a] = axis_ok[a] ? 1.0f / dlo[a] : 0.0f;
+        }
       }
+      auto packet_touches = [&](float lox, float loy, float loz, float hix, float hiy, float hiz) -> bool {
+        float tn = 0.0f, tf = tmax_all;
+        const float o3[3] = {ox, oy, oz}, lo3[3] = {lox, loy, loz}, hi3[3] = {hix, hiy, hiz};
+#pragma unroll
+        for (int a = 0; a < 3; a++) {
+          if (!axis_ok[a]) continue;
+          const float l = lo3[a] - o3[a], h = hi3[a] - o3[a];
+          const float p1 = l * ilo[a], p2 = l * ihi[a], p3 = h * ilo[a], p4 = h * ihi[a];
+          tn = fmaxf(tn, fminf(fminf(p1, p2), fminf(p3, p4)));
+          tf = fminf(tf, fmaxf(fmaxf(p1, p2), fmaxf(p3, p4)));
+        }
+        if (!(tn <= tf)) return false;
+        bool ok = true;
+#pragma unroll
+        for (int a = 0; a < 3; a++) {
+          if (axis_ok[a]) continue;
+          // positions reached on this axis for t in [0, tf]: between o + tf min(d_min, 0) and o + tf max(d_max, 0)
+          const float pmin = o3[a] + tf * fminf(dlo[a], 0.0f), pmax = o3[a] + tf * fmaxf(dhi[a], 0.0f);
+          const float pad = 1e-5f * (fabsf(pmin) + fabsf(pmax)) + 1e-7f;
+          ok &= (pmin - pad <= hi3[a]) & (pmax + pad >= lo3[a]);
+        }
+        return ok;
+      };
+      // while-while, as in closest_from: lanes walk down internal nodes until they hold a leaf, then test their leaves together
       int stack[kBvhStack];
       unsigned mstack[kBvhStack];
       int sp = 0;
       int ref = bv.root;
       unsigned alive = FULL;
-      for (;;) {
-        alive &= ~occ;
-        if (alive) {
-          if (ref >= 0) {
+      bool done = false;
+      while (!done) {
+        for (;;) {  // descend / pop until `ref` is a leaf that some live, unoccluded ray touches
+          alive &= ~occ;
+          if (alive && ref < 0) break;
+          if (alive) {
             const float4 *nd4 = bv.nodes + 4 * (size_t)ref;
             const float4 n0 = __ldg(nd4), n1 = __ldg(nd4 + 1), n2 = __ldg(nd4 + 2), n3 = __ldg(nd4 + 3);
-            unsigned m0 = 0u, m1 = 0u;
-#pragma unroll
-            for (int k = 0; k < CH; k++) {
-              if (!((alive >> k) & 1u)) continue;
-              if (box_entry(n0.x, n0.y, n0.z, n0.w, n1.x, n1.y, ox, oy, oz, ix[k], iy[k], iz[k], tm[k]) >= 0.0f) m0 |= 1u << k;
-              if (box_entry(n1.z, n1.w, n2.x, n2.y, n2.z, n2.w, ox, oy, oz, ix[k], iy[k], iz[k], tm[k]) >= 0.0f) m1 |= 1u << k;
-            }
+            const unsigned m0 = packet_touches(n0.x, n0.y, n0.z, n0.w, n1.x, n1.y) ? alive : 0u;
+            const unsigned m1 = packet_touches(n1.z, n1.w, n2.x, n2.y, n2.z, n2.w) ? alive : 0u;
             const int r0 = __float_as_int(n3.x), r1 = __float_as_int(n3.y);
             if (m0 && m1) {
               if (sp < kBvhStack) {
@@ -241,15 +294,23 @@ template <class T> struct BvhTracer {
               alive = m1;
               continue;
             }
-          } else {
-            const int first = (~ref) >> 3, cnt = ((~ref) & 7) + 1;
-            for (int k = 0; k < cnt; k++) {
-              const int s = first + k;
-              if (!casts_shadow(s)) continue;
-              shadow_pair<T, CH>(__ldg(bv.tri_a + s), __ldg(bv.tri_b + s), __ldg(bv.tri_c + s), start, rays, radius_sq, occ, alive);
-            }
-            if (occ == FULL) return occ;
           }
+          if (sp == 0) {
+            done = true;
+            break;
+          }
+          ref = stack[--sp];
+          alive = mstack[sp];
+        }
+        if (done) break;
+        {
+          const int first = (~ref) >> 3, cnt = ((~ref) & 7) + 1;
+          for (int k = 0; k < cnt; k++) {
+            const int s = first + k;
+            if (!casts_shadow(s)) continue;
+            shadow_pair<T, CH>(__ldg(bv.tri_a + s), __ldg(bv.tri_b + s), __ldg(bv.tri_c + s), start, rays, radius_sq, occ, alive);
+          }
+          if (occ == FULL) return occ;
         }
         if (sp == 0) break;
         ref = stack[--sp];
