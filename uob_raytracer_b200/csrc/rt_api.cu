@@ -214,6 +214,24 @@ int sphere_rects(FrameParams &fp) {
   return total;
 }
 
+int mesh_rect(const rt_ctx *ctx, FrameParams &fp) {
+  const int gx = (fp.W + kTileW - 1) / kTileW, gy = (fp.rows + kTileH - 1) / kTileH;
+  fp.n_rect = 0;
+  fp.rect_first[0] = fp.rect_first[1] = 0;
+  if (!(ctx->mesh_lo[0] <= ctx->mesh_hi[0])) return 0;  // the tree covers nothing
+  FrameParams q = fp;
+  visible_rect_of(ctx->mesh_lo, ctx->mesh_hi, q);  // whole frame when a corner of the box lies beside or behind the camera
+  const int y0 = std::max(q.vis_y0, fp.row0), y1 = std::min(q.vis_y1, fp.row0 + fp.rows);
+  if (q.vis_x0 >= q.vis_x1 || y0 >= y1) return 0;
+  int *r = fp.rect[0];
+  r[0] = q.vis_x0 / kTileW;
+  r[1] = (y0 - fp.row0) / kTileH;
+  r[2] = std::min(gx, (q.vis_x1 + kTileW - 1) / kTileW);
+  r[3] = std::min(gy, (y1 - fp.row0 + kTileH - 1) / kTileH);
+  fp.n_rect = 1;
+  return 4 * (r[2] - r[0]) * (r[3] - r[1]);
+}
+
 // Per-frame host work of the tuned kernels.  The constants of the exact primary test — b = cam - v0, det[b,e1,e2] and the
 // cofactors of det[-d,b,e2], det[-d,e1,b] (rt_fast.cuh) — depend on the camera position only; they are computed here
 // with the reference's single-rounded operation sequence (this file is compiled without FMA contraction; IEEE binary32 on

@@ -448,79 +448,103 @@ template <class T> __device__ __forceinline__ uint32_t pack_argb(V3<T> c) {
   return (255u << 24) + (r << 16) + (g << 8) + b;
 }
 
-// One pixel of `draw` (kernels.cl:368-428).  The direct light of a diffuse hit and the tail of
-// secondary_light (kernels.cl:342-365) share one call site: per ray, loop { miss -> black; diffuse ->
-// shade (x0.9 after a bounce) and stop; mirror/glass -> bounce, up to B times }.
+__device__ __forceinline__ float add_rn(float a, float b) { return __fadd_rn(a, b); }
+__device__ __forceinline__ float mul_rn(float a, float b) { return __fmul_rn(a, b); }
+__device__ __forceinline__ sfloat add_rn(sfloat a, sfloat b) { return a + b; }
+__device__ __forceinline__ sfloat mul_rn(sfloat a, sfloat b) { return a * b; }
+
+// One ray of a pixel of `draw` (kernels.cl:368-428): sub-pixel sample (dx, dy) of pixel (x, y).  The direct light of a
+// diffuse hit and the tail of secondary_light (kernels.cl:342-365) share one call site: loop { miss -> black; diffuse ->
+// shade (x0.9 after a bounce) and stop; mirror/glass -> bounce, up to B times }.  False: the ray adds nothing to the pixel.
 template <class T, int CH, class Tracer>
-__device__ __forceinline__ uint32_t shade_pixel(const Tracer &tr, const FrameParams &p, int x, int y) {
+__device__ __forceinline__ bool shade_sample(const Tracer &tr, const FrameParams &p, int x, int y, int dx, int dy, int global_id, V3<T> &contrib,
+                                             unsigned &n_shadow_calls, unsigned &n_bounce) {
   const T SW = T(__int2float_rn(p.W)), SH = T(__int2float_rn(p.H));
   const int A = p.A;
   const T fA = T(__int2float_rn(A));
-  // const int global_id = y*SCREEN_WIDTH + x  in float arithmetic (kernels.cl:380)
-  const int global_id = __float2int_rz(raw(T(__int2float_rn(y)) * SW + T(__int2float_rn(x))));
-  const V3<T> base(T(__int2float_rn(x * A)) - div_(SW * fA, T(2.0f)), T(__int2float_rn(y * A)) - div_(SH * fA, T(2.0f)), T(p.focal));
-  const V3<T> r0(T(p.rot[0]), T(p.rot[1]), T(p.rot[2])), r1(T(p.rot[3]), T(p.rot[4]), T(p.rot[5])), r2(T(p.rot[6]), T(p.rot[7]), T(p.rot[8]));
-  const V3<T> cam(T(p.cam[0]), T(p.cam[1]), T(p.cam[2])), light(T(p.light[0]), T(p.light[1]), T(p.light[2]));
+  const V3<T> light(T(p.light[0]), T(p.light[1]), T(p.light[2]));
+  V3<T> dir;
+  HitRec<T> hit;
+  hit.id = -1;
+  hit.color = make_float4(0.0f, 0.0f, 0.0f, 1.0f);
+  if constexpr (is_strict<T>::value) {
+    const V3<T> base(T(__int2float_rn(x * A)) - div_(SW * fA, T(2.0f)), T(__int2float_rn(y * A)) - div_(SH * fA, T(2.0f)), T(p.focal));
+    const V3<T> r0(T(p.rot[0]), T(p.rot[1]), T(p.rot[2])), r1(T(p.rot[3]), T(p.rot[4]), T(p.rot[5])), r2(T(p.rot[6]), T(p.rot[7]), T(p.rot[8]));
+    const V3<T> cam(T(p.cam[0]), T(p.cam[1]), T(p.cam[2]));
+    const V3<T> d0 = base + V3<T>(T(__int2float_rn(dx)), T(__int2float_rn(dy)), T(0.0f));
+    dir = normalize(V3<T>(dot(r0, d0), dot(r1, d0), dot(r2, d0)));
+    tr.closest(cam, dir, hit);
+  } else {
+    // Fast policy: the PRIMARY ray and its hit are still evaluated with the reference's exact sequence
+    // (a small part of the work), so that primary visibility is bit-identical to the reference — the
+    // default camera puts box edges exactly on pixel boundaries.
+    typedef sfloat S;
+    const S SWs(__int2float_rn(p.W)), SHs(__int2float_rn(p.H)), fAs(__int2float_rn(A));
+    const V3<S> bs(S(__int2float_rn(x * A)) - div_(SWs * fAs, S(2.0f)), S(__int2float_rn(y * A)) - div_(SHs * fAs, S(2.0f)), S(p.focal));
+    const V3<S> d0 = bs + V3<S>(S(__int2float_rn(dx)), S(__int2float_rn(dy)), S(0.0f));
+    const V3<S> s0(S(p.rot[0]), S(p.rot[1]), S(p.rot[2])), s1(S(p.rot[3]), S(p.rot[4]), S(p.rot[5])), s2(S(p.rot[6]), S(p.rot[7]), S(p.rot[8]));
+    const V3<S> ds = normalize(V3<S>(dot(s0, d0), dot(s1, d0), dot(s2, d0)));
+    HitRec<S> hs;
+    hs.id = -1;
+    hs.color = hit.color;
+    hs.point = V3<S>(S(0.0f), S(0.0f), S(0.0f));
+    hs.normal = hs.point;
+    tr.primary_strict(V3<S>(S(p.cam[0]), S(p.cam[1]), S(p.cam[2])), ds, hs);
+    dir = V3<T>(ds.x.v, ds.y.v, ds.z.v);
+    hit.id = hs.id;
+    hit.point = V3<T>(hs.point.x.v, hs.point.y.v, hs.point.z.v);
+    hit.normal = V3<T>(hs.normal.x.v, hs.normal.y.v, hs.normal.z.v);
+    hit.color = hs.color;
+  }
+  float medium = RT_AIR;
+  bool bounced = false;
+  int bounce = 0;
+  while (hit.id != -1) {
+    if (hit.color.w > 0.0f) {
+      const V3<T> dl = direct_light<T, CH, Tracer>(tr, hit.point, hit.normal, light, p.S, global_id);
+      n_shadow_calls++;
+      // (single-rounded operations under either policy: the one-ray-per-lane and the looped form of a pixel must agree)
+      const V3<T> lightv(add_rn(T(RT_INDIRECT), dl.x), add_rn(T(RT_INDIRECT), dl.y), add_rn(T(RT_INDIRECT), dl.z));
+      const V3<T> col = xyz<T>(hit.color);
+      // primary: colour*(indirect + direct) (kernels.cl:422); after a bounce: 0.9*light*colour (:355)
+      contrib = bounced ? V3<T>(mul_rn(mul_rn(T(0.9f), lightv.x), col.x), mul_rn(mul_rn(T(0.9f), lightv.y), col.y), mul_rn(mul_rn(T(0.9f), lightv.z), col.z))
+                        : V3<T>(mul_rn(col.x, lightv.x), mul_rn(col.y, lightv.y), mul_rn(col.z, lightv.z));
+      return true;
+    }
+    if (bounce >= p.B) break;
+    bounce++;
+    V3<T> start, ndir;
+    if (hit.color.w == 0.0f) reflect_ray<T>(dir, hit.normal, hit.point, start, ndir, medium);
+    else refract_ray<T>(dir, hit.normal, hit.point, medium, start, ndir, medium);
+    dir = ndir;
+    hit.id = -1;
+    hit.color.w = 1.0f;
+    tr.closest(start, dir, hit);
+    n_bounce++;
+    bounced = true;
+  }
+  return false;
+}
+
+// const int global_id = y*SCREEN_WIDTH + x  in float arithmetic (kernels.cl:380)
+template <class T> __device__ __forceinline__ int pixel_global_id(const FrameParams &p, int x, int y) {
+  return __float2int_rz(raw(T(__int2float_rn(y)) * T(__int2float_rn(p.W)) + T(__int2float_rn(x))));
+}
+
+// One pixel of `draw` (kernels.cl:368-428): its A*A rays one after the other, summed in the reference's order.
+template <class T, int CH, class Tracer>
+__device__ __forceinline__ uint32_t shade_pixel(const Tracer &tr, const FrameParams &p, int x, int y) {
+  const int A = p.A;
+  const int global_id = pixel_global_id<T>(p, x, y);
   V3<T> total(T(0.0f), T(0.0f), T(0.0f));
   unsigned n_shadow_calls = 0u, n_bounce = 0u;  // ray statistics (only reported with RT_FLAG_COUNT_RAYS)
 #pragma unroll 1
   for (int dy = 0; dy < A; dy++) {
 #pragma unroll 1
     for (int dx = 0; dx < A; dx++) {
-      V3<T> dir;
-      HitRec<T> hit;
-      hit.id = -1;
-      hit.color = make_float4(0.0f, 0.0f, 0.0f, 1.0f);
-      if constexpr (is_strict<T>::value) {
-        const V3<T> d0 = base + V3<T>(T(__int2float_rn(dx)), T(__int2float_rn(dy)), T(0.0f));
-        dir = normalize(V3<T>(dot(r0, d0), dot(r1, d0), dot(r2, d0)));
-        tr.closest(cam, dir, hit);
-      } else {
-        // Fast policy: the PRIMARY ray and its hit are still evaluated with the reference's exact sequence
-        // (a small part of the work), so that primary visibility is bit-identical to the reference — the
-        // default camera puts box edges exactly on pixel boundaries.
-        typedef sfloat S;
-        const S SWs(__int2float_rn(p.W)), SHs(__int2float_rn(p.H)), fAs(__int2float_rn(A));
-        const V3<S> bs(S(__int2float_rn(x * A)) - div_(SWs * fAs, S(2.0f)), S(__int2float_rn(y * A)) - div_(SHs * fAs, S(2.0f)), S(p.focal));
-        const V3<S> d0 = bs + V3<S>(S(__int2float_rn(dx)), S(__int2float_rn(dy)), S(0.0f));
-        const V3<S> s0(S(p.rot[0]), S(p.rot[1]), S(p.rot[2])), s1(S(p.rot[3]), S(p.rot[4]), S(p.rot[5])), s2(S(p.rot[6]), S(p.rot[7]), S(p.rot[8]));
-        const V3<S> ds = normalize(V3<S>(dot(s0, d0), dot(s1, d0), dot(s2, d0)));
-        HitRec<S> hs;
-        hs.id = -1;
-        hs.color = hit.color;
-        hs.point = V3<S>(S(0.0f), S(0.0f), S(0.0f));
-        hs.normal = hs.point;
-        tr.primary_strict(V3<S>(S(p.cam[0]), S(p.cam[1]), S(p.cam[2])), ds, hs);
-        dir = V3<T>(ds.x.v, ds.y.v, ds.z.v);
-        hit.id = hs.id;
-        hit.point = V3<T>(hs.point.x.v, hs.point.y.v, hs.point.z.v);
-        hit.normal = V3<T>(hs.normal.x.v, hs.normal.y.v, hs.normal.z.v);
-        hit.color = hs.color;
-      }
-      float medium = RT_AIR;
-      bool bounced = false;
-      int bounce = 0;
-      while (hit.id != -1) {
-        if (hit.color.w > 0.0f) {
-          const V3<T> dl = direct_light<T, CH, Tracer>(tr, hit.point, hit.normal, light, p.S, global_id);
-          n_shadow_calls++;
-          const V3<T> lightv(T(RT_INDIRECT) + dl.x, T(RT_INDIRECT) + dl.y, T(RT_INDIRECT) + dl.z);
-          // primary: colour*(indirect + direct) (kernels.cl:422); after a bounce: 0.9*light*colour (:355)
-          total = total + (bounced ? scale(T(0.9f), lightv) * xyz<T>(hit.color) : xyz<T>(hit.color) * lightv);
-          break;
-        }
-        if (bounce >= p.B) break;
-        bounce++;
-        V3<T> start, ndir;
-        if (hit.color.w == 0.0f) reflect_ray<T>(dir, hit.normal, hit.point, start, ndir, medium);
-        else refract_ray<T>(dir, hit.normal, hit.point, medium, start, ndir, medium);
-        dir = ndir;
-        hit.id = -1;
-        hit.color.w = 1.0f;
-        tr.closest(start, dir, hit);
-        n_bounce++;
-        bounced = true;
-      }
+      V3<T> c;
+      if (shade_sample<T, CH, Tracer>(tr, p, x, y, dx, dy, global_id, c, n_shadow_calls, n_bounce))
+        total = V3<T>(add_rn(total.x, c.x), add_rn(total.y, c.y), add_rn(total.z, c.z));
     }
   }
   if (p.ray_counters) {
@@ -529,6 +553,34 @@ __device__ __forceinline__ uint32_t shade_pixel(const Tracer &tr, const FramePar
     atomicAdd(p.ray_counters + 2, (unsigned long long)n_bounce);
   }
   const T fa = T(__int2float_rn(A * A));
+  return pack_argb<T>(V3<T>(div_(total.x, fa), div_(total.y, fa), div_(total.z, fa)));
+}
+
+// The same pixel by FOUR lanes (lane & 3 = which of the 2x2 rays; requires A == 2): each lane traces one ray, the four
+// contributions are added in the reference's order by every lane of the quad, so all four return the pixel.  A long ray
+// chain (a mesh behind a BVH: hundreds of dependent node fetches per ray) ends four times sooner, and the launch with it.
+// Called by all 32 lanes of a warp; `active` = this lane's pixel lies inside the launch.
+template <class T, int CH, class Tracer>
+__device__ __forceinline__ uint32_t shade_pixel_quad(const Tracer &tr, const FrameParams &p, int x, int y, bool active) {
+  const int lane = threadIdx.x & 31, q = lane & 3;
+  V3<T> c(T(0.0f), T(0.0f), T(0.0f));
+  unsigned n_shadow_calls = 0u, n_bounce = 0u;
+  bool has = false;
+  if (active) has = shade_sample<T, CH, Tracer>(tr, p, x, y, q & 1, q >> 1, pixel_global_id<T>(p, x, y), c, n_shadow_calls, n_bounce);
+  V3<T> total(T(0.0f), T(0.0f), T(0.0f));
+#pragma unroll
+  for (int k = 0; k < 4; k++) {
+    const int src = (lane & ~3) | k;
+    const bool hk = __shfl_sync(0xffffffffu, has ? 1 : 0, src) != 0;
+    const V3<T> ck(T(__shfl_sync(0xffffffffu, raw(c.x), src)), T(__shfl_sync(0xffffffffu, raw(c.y), src)), T(__shfl_sync(0xffffffffu, raw(c.z), src)));
+    if (hk) total = V3<T>(add_rn(total.x, ck.x), add_rn(total.y, ck.y), add_rn(total.z, ck.z));
+  }
+  if (p.ray_counters && active) {
+    atomicAdd(p.ray_counters + 0, 1ull);
+    atomicAdd(p.ray_counters + 1, (unsigned long long)n_shadow_calls * (unsigned long long)p.S);
+    atomicAdd(p.ray_counters + 2, (unsigned long long)n_bounce);
+  }
+  const T fa = T(4.0f);
   return pack_argb<T>(V3<T>(div_(total.x, fa), div_(total.y, fa), div_(total.z, fa)));
 }
 

@@ -196,13 +196,13 @@ __global__ void bvh_emit_kernel(int n, const int *__restrict__ left, const int *
 
 constexpr int kBigPrimaryMax = 32;  // big triangles handled by the camera-constant filter (one warp bins them)
 
-template <class T, int CH>
-__global__ void __launch_bounds__(kThreads) draw_bvh_kernel(const __grid_constant__ FrameParams p, const __grid_constant__ BvhView bv) {
-  __shared__ float4 s_prim[3 * kBigPrimaryMax];
-  __shared__ int s_plist[kBigPrimaryMax];
-  __shared__ int s_nlist;
+// QUAD blocks: 8x8-pixel sub-tiles with four lanes per pixel (one ray of the 2x2 each), the tiles the mesh can be seen in;
+// the other blocks: 16x16 tiles, one lane per pixel.  Same frame either way (rt_brute.cuh: shade_pixel_quad).
+template <class T, int CH, bool QUAD>
+__device__ __forceinline__ void draw_bvh_body(const FrameParams &p, const BvhView &bv, int bx, int by, float4 *s_prim, int *s_plist, int *s_nlist) {
   int x, y, tx, ty;
-  const bool in_frame = pixel_of_thread(p, x, y, tx, ty);
+  const bool in_frame = pixel_of_thread<QUAD>(p, bx, by, x, y, tx, ty);
+  constexpr int TW = QUAD ? kSplitTileW : kTileW, TH = QUAD ? kSplitTileH : kTileH;
   BvhTracer<T> tr;
   tr.bv = bv;
   const int n_big = bv.n - bv.n_bvh;
@@ -214,7 +214,7 @@ __global__ void __launch_bounds__(kThreads) draw_bvh_kernel(const __grid_constan
         const int lane = threadIdx.x, A = p.A;
         const float SW = (float)p.W, SH = (float)p.H, fA = (float)A;
         const float vx0 = (float)(tx * A) - SW * fA * 0.5f, vy0 = (float)(ty * A) - SH * fA * 0.5f;
-        const float vx1 = vx0 + (float)(kTileW * A - 1), vy1 = vy0 + (float)(kTileH * A - 1);
+        const float vx1 = vx0 + (float)(TW * A - 1), vy1 = vy0 + (float)(TH * A - 1);
         V3<float> dc[4];
         float dmax = 0.0f;
 #pragma unroll
@@ -236,17 +236,35 @@ __global__ void __launch_bounds__(kThreads) draw_bvh_kernel(const __grid_constan
         }
         const unsigned ballot = __ballot_sync(0xffffffffu, keep);
         if (keep) s_plist[__popc(ballot & ((1u << lane) - 1u))] = lane;
-        if (lane == 0) s_nlist = __popc(ballot);
+        if (lane == 0) *s_nlist = __popc(ballot);
       }
       __syncthreads();
       tr.big.prim = s_prim;
       tr.big.plist = s_plist;
-      tr.big.n_list = s_nlist;
+      tr.big.n_list = *s_nlist;
       tr.big.n_big = n_big;
     }
   }
-  if (!in_frame) return;
-  p.out[(size_t)y * p.W + x] = shade_pixel<T, CH, BvhTracer<T>>(tr, p, x, y);
+  if constexpr (QUAD) {
+    const uint32_t px = shade_pixel_quad<T, CH, BvhTracer<T>>(tr, p, x, y, in_frame);
+    if (in_frame && (threadIdx.x & 3) == 0) p.out[(size_t)y * p.W + x] = px;
+  } else {
+    if (!in_frame) return;
+    p.out[(size_t)y * p.W + x] = shade_pixel<T, CH, BvhTracer<T>>(tr, p, x, y);
+  }
+}
+
+template <class T, int CH>
+__global__ void __launch_bounds__(kThreads) draw_bvh_kernel(const __grid_constant__ FrameParams p, const __grid_constant__ BvhView bv) {
+  __shared__ float4 s_prim[3 * kBigPrimaryMax];
+  __shared__ int s_plist[kBigPrimaryMax];
+  __shared__ int s_nlist;
+  int bx, by;
+  if ((int)blockIdx.x < p.n_split) {  // the mesh's tiles first: they hold the longest rays of the frame
+    if (tile_of_block<true, true>(p, (int)blockIdx.x, bx, by)) draw_bvh_body<T, CH, true>(p, bv, bx, by, s_prim, s_plist, &s_nlist);
+  } else {
+    if (tile_of_block<false, true>(p, (int)blockIdx.x - p.n_split, bx, by)) draw_bvh_body<T, CH, false>(p, bv, bx, by, s_prim, s_plist, &s_nlist);
+  }
 }
 
 template <class T, int CH>
@@ -257,11 +275,17 @@ static cudaError_t launch_bvh_t(rt_ctx *ctx, const FrameParams &fp_in, cudaStrea
   fp.blk_stride = ctx->cfg.block_stride > 1 ? ctx->cfg.block_stride : 1;
   fp.blk_phase = ctx->cfg.block_stride > 1 ? ctx->cfg.block_phase : 0;
   fp.tile_order = tile_order_for(ctx, fp.row0, fp.rows, fp.grid_x, fp.n_blocks, kTileW, kTileH);
-  fp.n_split = 0;
+  // the tiles in which the mesh can be seen: four lanes per pixel (2x2 rays only), at the head of the launch
+  int n_sub = 0;
   fp.n_rect = 0;
-  const int my_blocks = (fp.n_blocks - fp.blk_phase + fp.blk_stride - 1) / fp.blk_stride;
+  fp.rect_first[0] = fp.rect_first[1] = 0;
+  if (fp.A == 2 && !(ctx->cfg.flags & RT_FLAG_NO_SPLIT)) n_sub = mesh_rect(ctx, fp);
+  const int my_tiles = fp.n_blocks > fp.blk_phase ? (fp.n_blocks - fp.blk_phase + fp.blk_stride - 1) / fp.blk_stride : 0;
+  const int my_split = n_sub > fp.blk_phase ? (n_sub - fp.blk_phase + fp.blk_stride - 1) / fp.blk_stride : 0;
+  fp.n_split = my_split;
+  const int my_blocks = my_tiles + my_split;
   char name[64];
-  snprintf(name, sizeof name, "draw_bvh_kernel<%s,%d>", is_strict<T>::value ? "sfloat" : "float", CH);
+  snprintf(name, sizeof name, "draw_bvh_kernel<%s,%d>%s", is_strict<T>::value ? "sfloat" : "float", CH, my_split ? "+quad" : "");
   ctx->last_kernel = name;
   if (my_blocks <= 0) return cudaSuccess;
   draw_bvh_kernel<T, CH><<<my_blocks, kThreads, 0, stream>>>(fp, *static_cast<const BvhView *>(ctx->bvh_view));
@@ -326,6 +350,25 @@ cudaError_t bvh_build(rt_ctx *ctx, const float *verts, const float *normals, con
     diag2 += ext[c] * ext[c];
   }
   const float big_diag2 = 0.35f * 0.35f * diag2;  // triangles longer than 35 % of the scene diagonal stay out of the tree
+  // bounds of what the tree will cover (same criterion as bvh_keys_kernel): where on the screen the long rays are
+  for (int c = 0; c < 3; c++) {
+    ctx->mesh_lo[c] = 3.4e38f;
+    ctx->mesh_hi[c] = -3.4e38f;
+  }
+  for (size_t t = 0; t < (size_t)n; t++) {
+    float tlo[3], thi[3], d2 = 0.0f;
+    for (int c = 0; c < 3; c++) {
+      const float a = verts[12 * t + c], b = verts[12 * t + 4 + c], cc = verts[12 * t + 8 + c];
+      tlo[c] = fminf(a, fminf(b, cc));
+      thi[c] = fmaxf(a, fmaxf(b, cc));
+      d2 += (thi[c] - tlo[c]) * (thi[c] - tlo[c]);
+    }
+    if (d2 > big_diag2) continue;
+    for (int c = 0; c < 3; c++) {
+      ctx->mesh_lo[c] = fminf(ctx->mesh_lo[c], tlo[c]);
+      ctx->mesh_hi[c] = fmaxf(ctx->mesh_hi[c], thi[c]);
+    }
+  }
   const float pad = 1e-5f * sqrtf(diag2);
 
   float4 *d_verts = nullptr, *d_normals = nullptr, *d_colors = nullptr;

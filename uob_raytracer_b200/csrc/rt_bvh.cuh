@@ -195,10 +195,8 @@ template <class T> struct BvhTracer {
       }
     }
     if (bv.n_bvh > 0) {
-      // Packet traversal: the CH rays share every node fetch; each node is tested against every ray
-      // that is still alive for it (slab test over 0 <= t <= |r|/|d_k|, the reference's distance
-      // limit), and a leaf tests only those rays.  A node is dropped when no live, unoccluded ray
-      // touches its (padded) box.
+      // Packet traversal: the CH rays share every node fetch and every box test; a leaf tests the rays that are not
+      // occluded yet.  A node is dropped when the packet as a whole cannot touch its (padded) box.
       const float ox = raw(start.x), oy = raw(start.y), oz = raw(start.z);
       const float R = sqrtf(raw(radius_sq));
       // The CH rays share their origin and differ by a jitter of a few per cent of |r|: ONE interval-arithmetic slab test
@@ -260,47 +258,29 @@ template <class T> struct BvhTracer {
       };
       // while-while, as in closest_from: lanes walk down internal nodes until they hold a leaf, then test their leaves together
       int stack[kBvhStack];
-      unsigned mstack[kBvhStack];
       int sp = 0;
       int ref = bv.root;
-      unsigned alive = FULL;
       bool done = false;
       while (!done) {
-        for (;;) {  // descend / pop until `ref` is a leaf that some live, unoccluded ray touches
-          alive &= ~occ;
-          if (alive && ref < 0) break;
-          if (alive) {
-            const float4 *nd4 = bv.nodes + 4 * (size_t)ref;
-            const float4 n0 = __ldg(nd4), n1 = __ldg(nd4 + 1), n2 = __ldg(nd4 + 2), n3 = __ldg(nd4 + 3);
-            const unsigned m0 = packet_touches(n0.x, n0.y, n0.z, n0.w, n1.x, n1.y) ? alive : 0u;
-            const unsigned m1 = packet_touches(n1.z, n1.w, n2.x, n2.y, n2.z, n2.w) ? alive : 0u;
-            const int r0 = __float_as_int(n3.x), r1 = __float_as_int(n3.y);
-            if (m0 && m1) {
-              if (sp < kBvhStack) {
-                stack[sp] = r1;
-                mstack[sp++] = m1;
-              }
-              ref = r0;
-              alive = m0;
-              continue;
-            }
-            if (m0) {
-              ref = r0;
-              alive = m0;
-              continue;
-            }
-            if (m1) {
-              ref = r1;
-              alive = m1;
-              continue;
-            }
-          }
-          if (sp == 0) {
+        while (ref >= 0) {  // descend / pop until `ref` is a leaf that the packet touches
+          const float4 *nd4 = bv.nodes + 4 * (size_t)ref;
+          const float4 n0 = __ldg(nd4), n1 = __ldg(nd4 + 1), n2 = __ldg(nd4 + 2), n3 = __ldg(nd4 + 3);
+          const bool m0 = packet_touches(n0.x, n0.y, n0.z, n0.w, n1.x, n1.y);
+          const bool m1 = packet_touches(n1.z, n1.w, n2.x, n2.y, n2.z, n2.w);
+          const int r0 = __float_as_int(n3.x), r1 = __float_as_int(n3.y);
+          if (m0 && m1) {
+            if (sp < kBvhStack) stack[sp++] = r1;
+            ref = r0;
+          } else if (m0) {
+            ref = r0;
+          } else if (m1) {
+            ref = r1;
+          } else if (sp > 0) {
+            ref = stack[--sp];
+          } else {
             done = true;
             break;
           }
-          ref = stack[--sp];
-          alive = mstack[sp];
         }
         if (done) break;
         {
@@ -308,13 +288,12 @@ template <class T> struct BvhTracer {
           for (int k = 0; k < cnt; k++) {
             const int s = first + k;
             if (!casts_shadow(s)) continue;
-            shadow_pair<T, CH>(__ldg(bv.tri_a + s), __ldg(bv.tri_b + s), __ldg(bv.tri_c + s), start, rays, radius_sq, occ, alive);
+            shadow_pair<T, CH>(__ldg(bv.tri_a + s), __ldg(bv.tri_b + s), __ldg(bv.tri_c + s), start, rays, radius_sq, occ, FULL & ~occ);
           }
           if (occ == FULL) return occ;
         }
         if (sp == 0) break;
         ref = stack[--sp];
-        alive = mstack[sp];
       }
     }
     shadow_spheres<T, CH>(start, rays, radius_sq, occ);

@@ -74,6 +74,7 @@ struct rt_ctx {
   struct TileOrder { int row0, rows, tile_w, tile_h; int *d_order; };
   std::vector<TileOrder> tile_orders;  // set by a launcher that needs shared memory beyond the scene
   float scene_lo[3] = {0, 0, 0}, scene_hi[3] = {0, 0, 0};  // bounding box of the triangles and the two spheres
+  float mesh_lo[3] = {0, 0, 0}, mesh_hi[3] = {0, 0, 0};    // BVH scenes: bounding box of the triangles the tree covers (rt_bvh.cu)
   std::string err;
 };
 

@@ -120,6 +120,8 @@ cudaError_t prepare_frame(rt_ctx *ctx, FrameParams &fp, cudaStream_t stream);
 // rt_api.cu: the sphere rectangles of a mixed launch for this camera and row range (fills fp.n_rect, fp.rect, fp.rect_first);
 // returns the number of 8x8 sub-tiles they hold.  Pure host arithmetic per launch: nothing is cached, copied or synchronised.
 int sphere_rects(FrameParams &fp);
+// rt_api.cu: BVH scenes — the one rectangle of tiles in which the mesh under the tree can be seen (same fields, same return value)
+int mesh_rect(const rt_ctx *ctx, FrameParams &fp);
 
 // float4 slots of the scene part of the fast kernel's shared memory (see brute_smem_bytes)
 __host__ __device__ inline int scene_smem_float4(int n, int n_sh) { return 12 * n + 5 * n_sh + ((kFastThreads / 32) * n + n_sh + 3) / 4 + 1; }
