@@ -17,4 +17,10 @@ if [ "${1:-}" = "ncu" ]; then
   python scripts/prof_run.py cfg2 4 > gpurun_out/prof_plain.log 2>&1 &&
   ncu --set full --clock-control none --import-source on -k regex:draw_ -s 2 -c 1 -f -o gpurun_out/prof python scripts/prof_run.py cfg2 4 > gpurun_out/prof_ncu.log 2>&1
   echo "ncu full rc=$?"
+  python scripts/prof_run.py cfg2 4 strict > gpurun_out/prof_strict_plain.log 2>&1 &&
+  ncu --set full --clock-control none --import-source on -k regex:draw_ -s 2 -c 1 -f -o gpurun_out/prof_strict python scripts/prof_run.py cfg2 4 strict > gpurun_out/prof_strict_ncu.log 2>&1
+  echo "ncu full strict rc=$?"
+  python scripts/prof_run.py cfg4 4 > gpurun_out/prof_cfg4_plain.log 2>&1 &&
+  ncu --set full --clock-control none --import-source on -k regex:draw_ -s 2 -c 1 -f -o gpurun_out/prof_cfg4 python scripts/prof_run.py cfg4 4 > gpurun_out/prof_cfg4_ncu.log 2>&1
+  echo "ncu full cfg4 rc=$?"
 fi

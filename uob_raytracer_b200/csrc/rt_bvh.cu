@@ -15,17 +15,22 @@ namespace rt {
 // build kernels
 // ---------------------------------------------------------------------------------------------
 
-__device__ __forceinline__ uint32_t expand_bits10(uint32_t v) {  // 10 bits -> every third bit
-  v = (v * 0x00010001u) & 0xFF0000FFu;
-  v = (v * 0x00000101u) & 0x0F00F00Fu;
-  v = (v * 0x00000011u) & 0xC30C30C3u;
-  v = (v * 0x00000005u) & 0x49249249u;
+__device__ __forceinline__ unsigned long long expand_bits21(unsigned long long v) {  // 21 bits -> every third bit
+  v &= 0x1fffffull;
+  v = (v | v << 32) & 0x1f00000000ffffull;
+  v = (v | v << 16) & 0x1f0000ff0000ffull;
+  v = (v | v << 8) & 0x100f00f00f00f00full;
+  v = (v | v << 4) & 0x10c30c30c30c30c3ull;
+  v = (v | v << 2) & 0x1249249249249249ull;
   return v;
 }
 
-// Per triangle (upload order): sort key.  Big triangles (box diagonal > big_diag) get bit 62 so
-// that they sort behind everything the tree covers; the index in the low word makes keys unique.
-__global__ void bvh_keys_kernel(const float4 *__restrict__ verts, int n, float3 lo, float3 inv_ext, float big_diag2,
+// Per triangle (upload order): sort key = [big flag | Morton code of the box centre, `bits` per axis | upload index, idx_bits].
+// Big triangles (box diagonal > big_diag) get bit 62 so that they sort behind everything the tree covers; the index in
+// the low bits makes keys unique.  The Morton grid spans the box of the small triangles and is as fine as 62 bits allow
+// (13 bits per axis at 1.3 M triangles: cells well below the size of a triangle, so neighbours in the order are
+// neighbours in space down to the leaves).
+__global__ void bvh_keys_kernel(const float4 *__restrict__ verts, int n, float3 lo, float3 inv_ext, float big_diag2, int bits, int idx_bits,
                                 unsigned long long *__restrict__ keys, int *__restrict__ vals, int *__restrict__ n_small) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
@@ -40,10 +45,11 @@ __global__ void bvh_keys_kernel(const float4 *__restrict__ verts, int n, float3 
   } else {
     const float cx = ((minx + maxx) * 0.5f - lo.x) * inv_ext.x, cy = ((miny + maxy) * 0.5f - lo.y) * inv_ext.y,
                 cz = ((minz + maxz) * 0.5f - lo.z) * inv_ext.z;
-    const uint32_t mx = (uint32_t)fminf(fmaxf(cx * 1024.0f, 0.0f), 1023.0f), my = (uint32_t)fminf(fmaxf(cy * 1024.0f, 0.0f), 1023.0f),
-                   mz = (uint32_t)fminf(fmaxf(cz * 1024.0f, 0.0f), 1023.0f);
-    const uint32_t morton = (expand_bits10(mx) << 2) | (expand_bits10(my) << 1) | expand_bits10(mz);
-    key = ((unsigned long long)morton << 32) | (unsigned)i;
+    const float cells = (float)(1u << bits), top = cells - 1.0f;
+    const unsigned long long mx = (unsigned long long)fminf(fmaxf(cx * cells, 0.0f), top), my = (unsigned long long)fminf(fmaxf(cy * cells, 0.0f), top),
+                             mz = (unsigned long long)fminf(fmaxf(cz * cells, 0.0f), top);
+    const unsigned long long morton = (expand_bits21(mx) << 2) | (expand_bits21(my) << 1) | expand_bits21(mz);
+    key = (morton << idx_bits) | (unsigned long long)(unsigned)i;
     atomicAdd(n_small, 1);
   }
   keys[i] = key;
@@ -254,8 +260,11 @@ __device__ __forceinline__ void draw_bvh_body(const FrameParams &p, const BvhVie
   }
 }
 
+#ifndef RT_BVH_MINBLOCKS  // resident blocks per SM the BVH kernel is compiled for; cfg4 fast / strict: 2 -> 1.48 / 2.73 ms, 3 -> 1.42 / 2.45, 4 -> 1.53 / 2.54
+#define RT_BVH_MINBLOCKS 3
+#endif
 template <class T, int CH>
-__global__ void __launch_bounds__(kThreads) draw_bvh_kernel(const __grid_constant__ FrameParams p, const __grid_constant__ BvhView bv) {
+__global__ void __launch_bounds__(kThreads, RT_BVH_MINBLOCKS) draw_bvh_kernel(const __grid_constant__ FrameParams p, const __grid_constant__ BvhView bv) {
   __shared__ float4 s_prim[3 * kBigPrimaryMax];
   __shared__ int s_plist[kBigPrimaryMax];
   __shared__ int s_nlist;
@@ -404,8 +413,18 @@ cudaError_t bvh_build(rt_ctx *ctx, const float *verts, const float *normals, con
   BVH_TRY(cudaMemsetAsync(d_counters, 0, 2 * sizeof(int), st));
 
   const int tpb = 256, blocks = (n + tpb - 1) / tpb;
-  bvh_keys_kernel<<<blocks, tpb, 0, st>>>(d_verts, n, make_float3(lo[0], lo[1], lo[2]),
-                                          make_float3(1.0f / ext[0], 1.0f / ext[1], 1.0f / ext[2]), big_diag2, d_keys, d_vals, d_counters);
+  int idx_bits = 1;
+  while (idx_bits < 31 && (1ll << idx_bits) < (long long)n) idx_bits++;
+  const int morton_bits = std::min(21, (62 - idx_bits) / 3);
+  float mlo[3], minv[3];  // Morton grid: the box of the small triangles (the scene box if there is none)
+  for (int c = 0; c < 3; c++) {
+    const bool have = ctx->mesh_lo[c] <= ctx->mesh_hi[c];
+    const float l = have ? ctx->mesh_lo[c] : lo[c], e = have ? ctx->mesh_hi[c] - ctx->mesh_lo[c] : ext[c];
+    mlo[c] = l;
+    minv[c] = 1.0f / (e > 0.0f ? e : 1.0f);
+  }
+  bvh_keys_kernel<<<blocks, tpb, 0, st>>>(d_verts, n, make_float3(mlo[0], mlo[1], mlo[2]), make_float3(minv[0], minv[1], minv[2]), big_diag2,
+                                          morton_bits, idx_bits, d_keys, d_vals, d_counters);
   BVH_TRY(cudaGetLastError());
   size_t sort_bytes = 0;
   BVH_TRY(cub::DeviceRadixSort::SortPairs(nullptr, sort_bytes, d_keys, d_keys2, d_vals, d_vals2, n, 0, 64, st));

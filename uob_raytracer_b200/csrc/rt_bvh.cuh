@@ -24,7 +24,10 @@
 
 namespace rt {
 
-constexpr int kBvhLeafMax = 4;       // triangles per leaf (<= 8 by the ref encoding)
+#ifndef RT_BVH_LEAF
+#define RT_BVH_LEAF 4
+#endif
+constexpr int kBvhLeafMax = RT_BVH_LEAF;  // triangles per leaf (<= 8 by the ref encoding)
 constexpr int kBvhStack = 64;
 
 struct BvhView {
