@@ -18,6 +18,20 @@
 #ifndef RT_FAST_CH
 #define RT_FAST_CH 8
 #endif
+// A/B switch, off.  Block prologue of a small scene (n <= 32, the Cornell box) with its latencies side by side instead of in a
+// row: 1 = the binning warp reads its triangle from global memory (L1 hits behind the staging loads) while the other warps
+// finish staging, and ONE barrier publishes both (instead of stage -> barrier -> one warp bins, seven wait -> barrier);
+// 2 = in addition the staging loads are issued before the launch-order table entry is waited for, i.e. before the
+// visible-rectangle exit.  ncu attributes 17 % of the stall samples to that chain, but both forms measured SLOWER on the
+// B200: cfg2 0.2061 -> 0.2057 (1) / 0.2082 (2) ms, cfg3 2.342 -> 2.369 / 2.375 ms — the other resident blocks already hide
+// the chain, and the empty tiles (44 % of a 16:9 frame) pay for staging they do not need.
+#ifndef RT_PROLOGUE_OVERLAP
+#define RT_PROLOGUE_OVERLAP 0
+#endif
+#ifndef RT_STAGE_UNROLL  // the staging loops run once or twice per thread: unrolled four times they were 365 instructions
+#define RT_STAGE_UNROLL 1
+#endif
+constexpr int kStageUnroll = RT_STAGE_UNROLL;
 
 namespace rt {
 
@@ -112,12 +126,20 @@ __device__ __forceinline__ void draw_fast_body(const FrameParams &p, const float
     }
     __syncthreads();
   }
+  constexpr int kTW = SPLIT ? kSplitTileW : kTileW, kTH = SPLIT ? kSplitTileH : kTileH;
+#ifdef RT_HOST_CONSTS_FAST
+  constexpr bool kHC = RT_HOST_CONSTS;
+#else
+  constexpr bool kHC = STRICT && RT_HOST_CONSTS;
+#endif
+  const bool small_scene = n <= 32;  // one warp bins a small scene on its own: no block-wide hand-shakes
+  const bool overlap = RT_PROLOGUE_OVERLAP && small_scene;
   int x, y, tile_x, tile_y;
   const bool in_frame = pixel_of_thread<SPLIT>(p, bx, by, x, y, tile_x, tile_y);
-  constexpr int kTW = SPLIT ? kSplitTileW : kTileW, kTH = SPLIT ? kSplitTileH : kTileH;
-  if (tile_x >= p.vis_x1 || tile_x + kTW <= p.vis_x0 || tile_y >= p.vis_y1 || tile_y + kTH <= p.vis_y0) {
-    // the tile lies outside the projection of the scene's bounding box (at 16:9 the bands beside the Cornell box,
-    // 44 % of the frame): A*A black samples per pixel (kernels.cl:404-425), without staging or binning anything
+  // the tile lies outside the projection of the scene's bounding box (at 16:9 the bands beside the Cornell box, 44 % of
+  // the frame): A*A black samples per pixel (kernels.cl:404-425), without binning anything
+  const bool outside_visible_rect = tile_x >= p.vis_x1 || tile_x + kTW <= p.vis_x0 || tile_y >= p.vis_y1 || tile_y + kTH <= p.vis_y0;
+  if (!(overlap && RT_PROLOGUE_OVERLAP >= 2) && outside_visible_rect) {  // before anything is staged
     if (in_frame) frame_of_row(p, y)[(size_t)y * p.W + x] = 0xff000000u;
     return;
   }
@@ -134,19 +156,19 @@ __device__ __forceinline__ void draw_fast_body(const FrameParams &p, const float
   // per-thread columns after the lists: parked primary hits (4 x 7 words), then the jitters (SINGLE only)
   float *const rec_base = reinterpret_cast<float *>(smem + scene_smem_float4(n, n_sh));
   float *const jit_base = rec_base + 4 * 7 * kThreads;
+#pragma unroll kStageUnroll
   for (int i = threadIdx.x; i < 5 * n; i += kThreads) gen[i] = scene[i];
   // Per-frame triangle constants: the bit-exact kernels take them from the host (rt_api.cu: prepare_frame — the same
   // single-rounded operations, done once per frame instead of once per block: 0.32 -> 0.30 ms on cfg2); the fast kernels
   // compute them in the block prologue as before — measured: the extra pointer and loads cost them 64 bytes more stack
   // (they are register-bound at 80 registers, three blocks per SM) and 5 % (cfg2) to 17 % (cfg3) of their speed.
-#ifdef RT_HOST_CONSTS_FAST
-  constexpr bool kHC = RT_HOST_CONSTS;
-#else
-  constexpr bool kHC = STRICT && RT_HOST_CONSTS;
-#endif
-  if constexpr (kHC)
+  if constexpr (kHC) {
+#pragma unroll kStageUnroll
     for (int i = threadIdx.x; i < 6 * n; i += kThreads) prim[i] = fconst[i];
+  }
+#pragma unroll kStageUnroll
   for (int i = threadIdx.x; i < 5 * n_sh + n; i += kThreads) shad[i] = scene[5 * n + 3 * n_sh + i];  // records, bounding spheres, plane records
+#pragma unroll kStageUnroll
   for (int i = threadIdx.x; i < n_sh; i += kThreads) full_list[i] = i;
   FastScene sc;
   sc.g.ta = gen;
@@ -165,11 +187,17 @@ __device__ __forceinline__ void draw_fast_body(const FrameParams &p, const float
   const V3<float> cam(p.cam[0], p.cam[1], p.cam[2]), light(p.light[0], p.light[1], p.light[2]);
   const int A = p.A, S = p.S;
   const float SW = (float)p.W, SH = (float)p.H, fA = (float)A;
-  if (threadIdx.x == 0) s_base = 0;
-  __syncthreads();
+  if (overlap) {
+    if (RT_PROLOGUE_OVERLAP >= 2 && outside_visible_rect) {  // block-uniform
+      if (in_frame) frame_of_row(p, y)[(size_t)y * p.W + x] = 0xff000000u;
+      return;
+    }
+  } else {
+    if (threadIdx.x == 0) s_base = 0;
+    __syncthreads();
+  }
 
   // ---- per-triangle camera constants + binning of the triangles against this block's tile ----
-  const bool small_scene = n <= 32;  // one warp bins a small scene on its own: no block-wide hand-shakes
   if (!small_scene || threadIdx.x < 32) {
     // corner rays of the tile in virtual (sub-pixel) coordinates, un-normalised (kernels.cl:384-400)
     const float vx0 = (float)(tile_x * A) - SW * fA * 0.5f;
@@ -220,10 +248,13 @@ __device__ __forceinline__ void draw_fast_body(const FrameParams &p, const float
       bool keep = false;
       if (lane < n) {
         if constexpr (!kHC) {
-          primary_constants(sc.g, prim, cam, lane);
+          if (overlap) primary_constants(scene[lane], scene[n + lane], scene[2 * n + lane], prim, cam, lane);  // (L1 hits: the staging loads just fetched these lines; this lane's own prim[] writes need no barrier to be read back)
+          else primary_constants(sc.g, prim, cam, lane);
           if constexpr (!STRICT) primary_affine(prim, aff, lane, p.rot, p.focal, dmax);
+          keep = tile_may_hit(prim, lane, dc, dmax);
+        } else {
+          keep = tile_may_hit(overlap ? fconst : prim, lane, dc, dmax);  // overlap: the staged copy is not published yet
         }
-        keep = tile_may_hit(prim, lane, dc, dmax);
       }
       const unsigned ballot = __ballot_sync(0xffffffffu, keep);
       if (keep) plist[__popc(ballot & ((1u << lane) - 1u))] = lane;

@@ -134,9 +134,8 @@ __device__ __forceinline__ bool box_may_be_shadowed_by(const float4 *shad, const
 // Per-triangle constants of rays starting at `cam`, with the reference's (strict) operation
 // sequence, so the confirm step reproduces the reference's decisions bit for bit.
 // g bounds the rounding error of the filter's dot products: 2e-6 * max L1 norm (|d_i| <= 1).
-__device__ __forceinline__ void primary_constants(const SceneView &g, float4 *prim, V3<float> cam, int i) {
+__device__ __forceinline__ void primary_constants(float4 A, float4 Bq, float4 C, float4 *prim, V3<float> cam, int i) {
   typedef sfloat S;
-  const float4 A = g.ta[i], Bq = g.tb[i], C = g.tc[i];
   const V3<S> b(S(cam.x) - S(A.x), S(cam.y) - S(A.y), S(cam.z) - S(A.z));
   const V3<S> e1 = xyz<S>(Bq), e2 = xyz<S>(C);
   const S detA0 = (b.x * S(A.w) - b.y * S(Bq.w)) + b.z * S(C.w);
@@ -148,6 +147,9 @@ __device__ __forceinline__ void primary_constants(const SceneView &g, float4 *pr
   prim[3 * i + 0] = make_float4(A.w, Bq.w, C.w, detA0.v);
   prim[3 * i + 1] = make_float4(U0.v, U1.v, U2.v, tol);
   prim[3 * i + 2] = make_float4(V0.v, V1.v, V2.v, 3.0f * tol);
+}
+__device__ __forceinline__ void primary_constants(const SceneView &g, float4 *prim, V3<float> cam, int i) {
+  primary_constants(g.ta[i], g.tb[i], g.tc[i], prim, cam, i);
 }
 
 // Can triangle i be hit by any ray of a tile whose four corner rays (un-normalised) are dc[0..3]?
@@ -493,6 +495,7 @@ __device__ __forceinline__ void closest_hit_bounce(const SceneView &sc, V3<float
 // The S jitters of a pixel: they depend on the pixel id only (kernels.cl:319,331).
 template <int CH> struct Jitters {  // in registers
   static constexpr bool kPacked = false;
+  static constexpr bool kIndexable = false;  // a loop over the samples must be fully unrolled (no dynamic register index)
   float x[CH], y[CH], z[CH];
   __device__ __forceinline__ float jx(int k) const { return x[k]; }
   __device__ __forceinline__ float jy(int k) const { return y[k]; }
@@ -510,6 +513,7 @@ template <int CH, int STRIDE> struct JittersShared {
 #else
   static constexpr bool kPacked = false;
 #endif
+  static constexpr bool kIndexable = true;
   float *p;  // this thread's column: base + thread (odd CH) or base + 2*thread (even CH)
   __device__ __forceinline__ static float *column(float *base, int thread) { return base + (kPacked ? 2 * thread : thread); }
   __device__ __forceinline__ int at(int c, int k) const { return kPacked ? 2 * STRIDE * (c * (CH / 2) + (k >> 1)) + (k & 1) : (3 * k + c) * STRIDE; }
@@ -585,6 +589,27 @@ __device__ __forceinline__ void make_jitters_shared(int global_id, const Jitters
 
 // Number of UNOCCLUDED samples among the CH shadow rays start + t (r + j_k)  (in_shadow, kernels.cl:243-311).
 // The directions d_k = r + j_k are never materialised: d_k.X = r.X + j_k.X with r.X once per (point, triangle).
+// Code size.  The dominant kernel is ~5 000 SASS instructions (79 KB) against a 32 KB instruction cache per SM, and its
+// warps run in different phases: ncu shows ~10 % of the stall samples as "no instruction".  Rare paths therefore stay
+// rolled: the mirror sphere's per-sample shadow test below was 550 instructions (11 % of the kernel) fully unrolled and
+// is executed for the few points whose ray cone touches the sphere — rolled: cfg2 -1.2 %, cfg3 -2.3 % (same frames).
+// -DRT_SPHERE_SHADOW_ROLLED=0 restores the unrolled form.
+#ifndef RT_SPHERE_SHADOW_ROLLED
+#define RT_SPHERE_SHADOW_ROLLED 1
+#endif
+// Registers.  The kernel is compiled for 80 registers (three blocks per SM) and the shadow loop is where it needs most.
+// Until round 2 it cached |d_k|^2 of the CH samples of a shading point in CH registers, filled on first use; recomputing
+// the value where it is needed (three adds, one multiply, two FMAs on jitters that are in shared memory anyway — the same
+// operations, hence the same bits) frees them: cfg2 0.2002 -> 0.1916 ms, cfg3 2.302 -> 2.111 ms, HEAD 0.205 -> 0.188 ms.
+// -DRT_DD_CACHE=1 restores the cache.
+#ifndef RT_DD_CACHE
+#define RT_DD_CACHE 0
+#endif
+#ifndef RT_SAMPLE_UNROLL  // A/B switch: unroll factor of the per-sample triangle test (0 = fully)
+#define RT_SAMPLE_UNROLL 0
+#endif
+constexpr int kSampleUnroll = RT_SAMPLE_UNROLL;
+constexpr bool kSphereShadowRolled = RT_SPHERE_SHADOW_ROLLED;
 template <int CH, class J>
 __device__ __forceinline__ int shadow_lit_count(const FastScene &sc, V3<float> start, V3<float> r, float radius_sq,
                                                 const J &j, unsigned valid_mask) {
@@ -597,6 +622,9 @@ __device__ __forceinline__ int shadow_lit_count(const FastScene &sc, V3<float> s
   float2 dd2[P ? CH / 2 : 1];
   bool have_dd = false;
   auto need_dd = [&]() {
+#if !RT_DD_CACHE
+    if constexpr (!P) return;
+#endif
     if (have_dd) return;
     have_dd = true;
     if constexpr (P) {
@@ -616,7 +644,14 @@ __device__ __forceinline__ int shadow_lit_count(const FastScene &sc, V3<float> s
   };
   auto dd_of = [&](int k) -> float {
     if constexpr (P) return (k & 1) ? dd2[k >> 1].y : dd2[k >> 1].x;
+#if !RT_DD_CACHE  // |d_k|^2 recomputed where it is used (same operations)
+    else {
+      const float ddx = r.x + j.jx(k), ddy = r.y + j.jy(k), ddz = r.z + j.jz(k);
+      return fmaf(ddz, ddz, fmaf(ddx, ddx, __fmul_rn(ddy, ddy)));
+    }
+#else
     else return dd[k];
+#endif
   };
   // |r| / |d_s| <= R / (R - jmax); no bound (k huge) when the light is closer than 2 jmax
   const float R = sqrt_approx(radius_sq);
@@ -680,7 +715,7 @@ __device__ __forceinline__ int shadow_lit_count(const FastScene &sc, V3<float> s
         }
       }
     } else {
-#pragma unroll
+#pragma unroll((kSampleUnroll > 0 && J::kIndexable) ? kSampleUnroll : CH)
       for (int k = 0; k < CH; k++) {
         const float jx = j.jx(k), jy = j.jy(k), jz = j.jz(k);
         const float dn = fmaf(jx, c0, fmaf(-jy, c1, fmaf(jz, c2, rN)));
@@ -688,7 +723,7 @@ __device__ __forceinline__ int shadow_lit_count(const FastScene &sc, V3<float> s
         const float E2 = fmaf(jx, V.x, fmaf(jy, V.y, fmaf(jz, V.z, rV)));
         const unsigned dnb = __float_as_uint(dn);
         const unsigned sx = ((__float_as_uint(E1) ^ dnb) | (__float_as_uint(E2) ^ dnb)) | ~(numb ^ dnb);
-        const bool hit = ((int)sx >= 0) & (fabsf(__fadd_rn(E1, E2)) <= fabsf(dn)) & (__fmul_rn(q1, dd[k]) < __fmul_rn(dn, dn));
+        const bool hit = ((int)sx >= 0) & (fabsf(__fadd_rn(E1, E2)) <= fabsf(dn)) & (__fmul_rn(q1, dd_of(k)) < __fmul_rn(dn, dn));
         occ |= hit ? (1u << k) : 0u;
       }
     }
@@ -707,11 +742,19 @@ __device__ __forceinline__ int shadow_lit_count(const FastScene &sc, V3<float> s
     const float perp2 = LL - Lr * Lr * inv_r2;
     const float lim = kSlack * sqrt_approx(cr.w) + sqrt_approx(LL) * (kk * kJitterMax * rcp_approx(R));
     if (perp2 > lim * lim) continue;
-    need_dd();
-#pragma unroll
+    // (jitters in shared memory: a rolled loop, |d_k|^2 recomputed from the jitters with the same operations — see above)
+    constexpr bool kRolled = kSphereShadowRolled && J::kIndexable && !P;
+    if constexpr (!kRolled) need_dd();
+#pragma unroll(kRolled ? 1 : CH)
     for (int k = 0; k < CH; k++) {
       if ((occ >> k) & 1u) continue;
-      const float a = dd_of(k);
+      float a;
+      if constexpr (kRolled) {
+        const float ddx = r.x + j.jx(k), ddy = r.y + j.jy(k), ddz = r.z + j.jz(k);
+        a = fmaf(ddz, ddz, fmaf(ddx, ddx, __fmul_rn(ddy, ddy)));
+      } else {
+        a = dd_of(k);
+      }
       const float b = __fmul_rn(2.0f, fmaf(j.jx(k), L.x, fmaf(j.jy(k), L.y, fmaf(j.jz(k), L.z, Lr))));
       const float disc = fmaf(b, b, -__fmul_rn(__fmul_rn(4.0f, a), c));
       if (disc < 0.0f) continue;
@@ -838,7 +881,7 @@ __device__ __forceinline__ unsigned shadow_occ_strict(const FastScene &sc, V3<sf
     }
     const V3<T> L = start_s - xyz<T>(cr);
     const T c = dot(L, L) - T(cr.w);
-#pragma unroll
+#pragma unroll((kSphereShadowRolled && J::kIndexable) ? 1 : CH)
     for (int k = 0; k < CH; k++) {  // kernels.cl:278-307, as shadow_spheres<sfloat>
       if ((occ >> k) & 1u) continue;
       const V3<T> d = r_s + V3<T>(T(j.jx(k)), T(j.jy(k)), T(j.jz(k)));

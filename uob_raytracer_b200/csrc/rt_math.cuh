@@ -59,12 +59,21 @@ __device__ __forceinline__ float sqrt_approx(float x) {
 // Fast path: IEEE-rounded (used only on the closest-hit path, ~10 % of the
 // work, where knife-edge decisions at the default camera are rounding
 // sensitive — SURVEY.md §7); the shadow path uses division-free tests.
+#ifdef RT_STRICT_NOINLINE  // A/B switch (code size): one out-of-line copy of each correctly rounded sequence per kernel
+static __device__ __noinline__ float rt_frcp_rn(float x) { return __frcp_rn(x); }
+static __device__ __noinline__ float rt_fdiv_rn(float a, float b) { return __fdiv_rn(a, b); }
+static __device__ __noinline__ float rt_fsqrt_rn(float x) { return __fsqrt_rn(x); }
+#else
+#define rt_frcp_rn __frcp_rn
+#define rt_fdiv_rn __fdiv_rn
+#define rt_fsqrt_rn __fsqrt_rn
+#endif
 __device__ __forceinline__ float rcp_(float x) { return __frcp_rn(x); }
-__device__ __forceinline__ sfloat rcp_(sfloat x) { return sfloat(__frcp_rn(x.v)); }  // rcp.rn: correctly rounded == 1.0f/x
+__device__ __forceinline__ sfloat rcp_(sfloat x) { return sfloat(rt_frcp_rn(x.v)); }  // rcp.rn: correctly rounded == 1.0f/x
 __device__ __forceinline__ float div_(float a, float b) { return __fdiv_rn(a, b); }
-__device__ __forceinline__ sfloat div_(sfloat a, sfloat b) { return sfloat(__fdiv_rn(a.v, b.v)); }
+__device__ __forceinline__ sfloat div_(sfloat a, sfloat b) { return sfloat(rt_fdiv_rn(a.v, b.v)); }
 __device__ __forceinline__ float sqrt_(float x) { return __fsqrt_rn(x); }
-__device__ __forceinline__ sfloat sqrt_(sfloat x) { return sfloat(__fsqrt_rn(x.v)); }
+__device__ __forceinline__ sfloat sqrt_(sfloat x) { return sfloat(rt_fsqrt_rn(x.v)); }
 __device__ __forceinline__ float abs_(float x) { return fabsf(x); }
 __device__ __forceinline__ sfloat abs_(sfloat x) { return sfloat(fabsf(x.v)); }
 // OpenCL min/max semantics (oracle/cl_shim.h): min(x,y) = y<x?y:x, max(x,y) = x<y?y:x
