@@ -16,7 +16,8 @@ def child(reps: int, with_mesh: bool):
     rot, cam4, light4 = cam.rot(), cam.position.copy(), cam.light.copy()
     out = {}
     cases = [("head", 1024, 1024, 2, 10, 10, {}), ("cfg2", 1920, 1080, 2, 8, 10, {}), ("cfg3", 3840, 2160, 4, 10, 4, {}),
-             ("cfg2_1of8", 1920, 1080, 2, 8, 10, dict(block_stride=8, block_phase=3))]
+             ("cfg2_1of8", 1920, 1080, 2, 8, 10, dict(block_stride=8, block_phase=3)),
+             ("cfg2_s4", 1920, 1080, 2, 4, 10, {})]  # four shadow samples: 51 KB of shared memory per block, four blocks fit an SM
     for name, W, H, A, S, B, kw in cases:
         f = 1100.0 * A * H / 1024
         for strict in (False, True):

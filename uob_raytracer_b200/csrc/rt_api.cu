@@ -733,9 +733,17 @@ int rt_render(rt_ctx *ctx, const float rot12[12], const float cam[4], const floa
     return RT_ERR_INVALID;
   }
   const int W = ctx->cfg.width;
-  // Band height: a multiple of the block height, about a quarter of the tile.  Small tiles and
-  // block-interleaved contexts (whose frame is completed by other GPUs) render in one piece.
-  int band_rows = ((ctx->rows + rt_ctx::kBands - 1) / rt_ctx::kBands + 15) / 16 * 16;
+  // Band height: a multiple of the block height.  Small tiles and block-interleaved contexts (whose frame is completed
+  // by other GPUs) render in one piece.  The exposed part of the read-back is the last band's copy, so more bands hide
+  // more of it — until the bands are such small launches that the kernels lose more than the copy gains.  Measured on
+  // B200 (scripts/gpu_e2e_variants.sh, ms per frame for 2 / 3 / 4 / 5 / 6 / 8 bands): 1080p cfg2 0.303 / 0.276 / 0.267 /
+  // 0.260 / 0.261 / 0.254; 4K cfg3 - / - / 2.302 / 2.277 / 2.345 / 2.35.
+#ifdef RT_BANDS
+  const int n_bands = RT_BANDS < rt_ctx::kBands ? RT_BANDS : rt_ctx::kBands;
+#else
+  const int n_bands = (size_t)W * ctx->rows <= (size_t)3 << 20 ? 8 : 5;
+#endif
+  int band_rows = ((ctx->rows + n_bands - 1) / n_bands + 15) / 16 * 16;
   if (ctx->rows < 256 || ctx->cfg.block_stride > 1 || ctx->d_ray_counters) band_rows = ctx->rows;
   if (band_rows >= ctx->rows) {
     int rc = render_impl(ctx, rot12, cam, light, focal, nullptr, ctx->stream);

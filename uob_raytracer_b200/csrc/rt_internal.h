@@ -18,12 +18,10 @@ struct rt_ctx {
   cudaStream_t stream = nullptr;      // the stream in use
   cudaStream_t own_stream = nullptr;  // created by rt_create
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
-  // rt_render overlaps the read-back with the kernel: the tile is rendered in kBands row bands on
-  // their own streams and each band is copied to the host as soon as it is done
-  #ifndef RT_BANDS
-#define RT_BANDS 4
-#endif
-  static constexpr int kBands = RT_BANDS;
+  // rt_render overlaps the read-back with the kernel: the tile is rendered in row bands (at most kBands) on
+  // their own streams and each band is copied to the host as soon as it is done.  How many: rt_api.cu, band_count
+  // (-DRT_BANDS=n forces a count, for A/B runs).
+  static constexpr int kBands = 8;
   cudaStream_t band_stream[kBands] = {};
   cudaEvent_t band_done[kBands] = {};
   cudaEvent_t band_start = nullptr;
