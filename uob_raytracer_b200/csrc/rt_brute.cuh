@@ -167,14 +167,31 @@ __device__ __forceinline__ void closest_spheres(V3<T> start, V3<T> dir, T curren
 }
 
 // |d_k|^2 of the CH shadow directions (fast policy only)
+// (RT_RAYS_DD_CACHE=1 keeps |d_k|^2 in CH more registers; recomputed at its two uses it is three operations, spelled out so
+// that every inlined copy rounds alike — the BVH kernel carries the rays through a traversal with a 64-entry stack and is
+// register-bound at 80; see rt_fast.cuh: RT_DD_CACHE for the same change in the brute-force kernel)
+#ifndef RT_RAYS_DD_CACHE
+#define RT_RAYS_DD_CACHE 0
+#endif
 template <class T, int CH> struct ShadowRays {
   V3<T> d[CH];
+#if RT_RAYS_DD_CACHE
   T dd[CH];
+#endif
   __device__ __forceinline__ void finish() {
+#if RT_RAYS_DD_CACHE
     if constexpr (!is_strict<T>::value) {
 #pragma unroll
-      for (int k = 0; k < CH; k++) dd[k] = d[k].x * d[k].x + d[k].y * d[k].y + d[k].z * d[k].z;
+      for (int k = 0; k < CH; k++) dd[k] = fmaf(raw(d[k].z), raw(d[k].z), fmaf(raw(d[k].x), raw(d[k].x), __fmul_rn(raw(d[k].y), raw(d[k].y))));
     }
+#endif
+  }
+  __device__ __forceinline__ float dd_of(int k) const {
+#if RT_RAYS_DD_CACHE
+    return raw(dd[k]);
+#else
+    return fmaf(raw(d[k].z), raw(d[k].z), fmaf(raw(d[k].x), raw(d[k].x), __fmul_rn(raw(d[k].y), raw(d[k].y))));
+#endif
   }
 };
 
@@ -212,7 +229,7 @@ __device__ __forceinline__ void shadow_pair(float4 A, float4 Bq, float4 C, V3<T>
       // den = det[-d, e1, e2];  t = detA0/den
       const T den = -((rays.d[k].x * c0 - rays.d[k].y * c1) + rays.d[k].z * c2);
       // t >= 0  and  t^2 |d|^2 < r^2, without dividing (den == 0 fails the second test)
-      const bool s1 = (detA0 * den >= 0.0f) && (num2 * rays.dd[k] < radius_sq * (den * den)) && ((alive >> k) & 1u);
+      const bool s1 = (detA0 * den >= 0.0f) && (num2 * rays.dd_of(k) < radius_sq * (den * den)) && ((alive >> k) & 1u);
       if (s1) {
         const T sg = (den < 0.0f) ? -1.0f : 1.0f;
         const T D1 = -((rays.d[k].x * U0 - rays.d[k].y * U1) + rays.d[k].z * U2) * sg;  // u * |den|
@@ -262,7 +279,7 @@ __device__ __forceinline__ void shadow_pair_culled(float4 A, float4 Bq, float4 C
     const float E1 = dot(d, U), E2 = dot(d, V);
     const unsigned dnb = __float_as_uint(dn);
     const unsigned sx = ((__float_as_uint(E1) ^ dnb) | (__float_as_uint(E2) ^ dnb)) | ~(numb ^ dnb);
-    const bool hit = ((int)sx >= 0) & (fabsf(E1 + E2) <= fabsf(dn)) & (q1 * rays.dd[k] < dn * dn) & (((alive >> k) & 1u) != 0u);
+    const bool hit = ((int)sx >= 0) & (fabsf(E1 + E2) <= fabsf(dn)) & (q1 * rays.dd_of(k) < dn * dn) & (((alive >> k) & 1u) != 0u);
     occ |= hit ? (1u << k) : 0u;
   }
 }
