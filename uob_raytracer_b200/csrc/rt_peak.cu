@@ -51,16 +51,49 @@ __global__ void peer_wait_kernel(const uint32_t *flags, int n, uint32_t value, i
 struct PeerCounters {
   uint32_t *c[8];
 };
-__global__ void peer_add_kernel(PeerCounters pc) {
-  // Everything this stream did before (the draw kernel's stores into the peers' frames) happened-before this kernel; the
-  // system-scope fence makes it visible to the other GPUs before the count is.
+// Launched as a PROGRAMMATIC DEPENDENT of the draw kernel in front of it (cudaLaunchAttributeProgrammaticStreamSerialization):
+// its one block is scheduled while the draw kernel is still running and parks in griddepcontrol.wait, which returns once
+// that grid has completed and its memory operations are performed — so the delivery is reported without the launch gap
+// of an ordinary stream-ordered kernel behind a 40-100 us draw kernel (measured on two B200s: -DRT_PDL_SIGNAL=0 restores
+// the plain launch).  Without a kernel in front of it on the stream the wait returns at once.
+#ifndef RT_PDL_SIGNAL
+#define RT_PDL_SIGNAL 1
+#endif
+#ifndef RT_SIGNAL_SC_FENCE
+#define RT_SIGNAL_SC_FENCE 0
+#endif
+__global__ void peer_add_kernel(const __grid_constant__ PeerCounters pc) {
+#if RT_PDL_SIGNAL
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+#endif
+  // Everything this stream did before (the draw kernel's stores into the peers' frames) happened-before this point, and a
+  // release at system scope is cumulative: whoever acquires the count sees those stores.  (red.release.sys carries its own
+  // MEMBAR.ALL.SYS; a sequentially consistent __threadfence_system() in front of it — -DRT_SIGNAL_SC_FENCE=1, the form
+  // of round 1 — is a second, slower system barrier that orders nothing more here.)
+#if RT_SIGNAL_SC_FENCE
   __threadfence_system();
+#endif
   asm volatile("red.release.sys.global.add.u32 [%0], 1;" ::"l"(pc.c[threadIdx.x]) : "memory");
 }
 
 cudaError_t launch_peer_add_many(uint32_t *const *counters, int n, cudaStream_t stream) {
   PeerCounters pc{};
   for (int i = 0; i < n && i < 8; i++) pc.c[i] = counters[i];
+#if RT_PDL_SIGNAL
+  cudaLaunchConfig_t lc = {};
+  lc.gridDim = dim3(1);
+  lc.blockDim = dim3((unsigned)n);
+  lc.dynamicSmemBytes = 0;
+  lc.stream = stream;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  lc.attrs = at;
+  lc.numAttrs = 1;
+  cudaError_t e = cudaLaunchKernelEx(&lc, peer_add_kernel, pc);
+  if (e == cudaSuccess) return e;
+  cudaGetLastError();  // (attribute not accepted: plain launch)
+#endif
   peer_add_kernel<<<1, n, 0, stream>>>(pc);
   return cudaGetLastError();
 }
